@@ -1,0 +1,62 @@
+// Shared host-side helpers for the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/cppflow_b200.h"
+#include "robots.cuh"
+#include "geom.cuh"
+
+namespace cppflow {
+
+void set_last_error(const char* msg);
+int fail(int code, const char* fmt, ...);
+
+#define CPPFLOW_CHECK_ARG(cond, what)                                        \
+    do {                                                                     \
+        if (!(cond)) return ::cppflow::fail(CPPFLOW_E_INVALID, "%s: invalid argument: %s", __func__, what); \
+    } while (0)
+
+#define CPPFLOW_CHECK_LAUNCH()                                               \
+    do {                                                                     \
+        cudaError_t e_ = cudaGetLastError();                                 \
+        if (e_ != cudaSuccess)                                               \
+            return ::cppflow::fail(CPPFLOW_E_CUDA, "%s: CUDA error: %s", __func__, cudaGetErrorString(e_)); \
+    } while (0)
+
+// run `body` with `M` bound to the robot model type
+#define CPPFLOW_DISPATCH_ROBOT(robot, ...)                                   \
+    switch (robot) {                                                         \
+        case ::cppflow::ROBOT_FETCH: { using M = ::cppflow::Fetch; __VA_ARGS__; } break;        \
+        case ::cppflow::ROBOT_FETCH_ARM: { using M = ::cppflow::FetchArm; __VA_ARGS__; } break; \
+        case ::cppflow::ROBOT_PANDA: { using M = ::cppflow::Panda; __VA_ARGS__; } break;        \
+        default: return ::cppflow::fail(CPPFLOW_E_INVALID, "%s: unknown robot id %d", __func__, robot); \
+    }
+
+inline int make_obstacles(const float* h_cuboids, const float* h_Tcuboids, int n, Obstacles& ob) {
+    std::memset(&ob, 0, sizeof(ob));
+    if (n < 0 || n > CPPFLOW_MAX_OBSTACLES) return fail(CPPFLOW_E_INVALID, "n_obstacles %d out of range [0,8]", n);
+    if (n > 0 && (!h_cuboids || !h_Tcuboids)) return fail(CPPFLOW_E_INVALID, "null obstacle tables");
+    ob.n = n;
+    for (int o = 0; o < n; ++o) {
+        const float* c = h_cuboids + 6 * o;
+        const float* T = h_Tcuboids + 16 * o;
+        bool rot = false;
+        for (int r = 0; r < 3; ++r) {
+            ob.lo[o][r] = c[r];
+            ob.hi[o][r] = c[3 + r];
+            ob.t[o][r] = T[4 * r + 3];
+            for (int k = 0; k < 3; ++k) {
+                ob.R[o][3 * r + k] = T[4 * r + k];
+                if (T[4 * r + k] != (r == k ? 1.f : 0.f)) rot = true;
+            }
+        }
+        ob.has_rot[o] = rot ? 1 : 0;
+    }
+    return CPPFLOW_OK;
+}
+
+inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+}  // namespace cppflow

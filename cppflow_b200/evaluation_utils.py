@@ -1,0 +1,60 @@
+"""Joint-change / pose-error metrics with the reference's names (cppflow/evaluation_utils.py)."""
+from typing import List, Tuple
+
+import numpy as np
+import torch
+
+
+def angular_changes(qpath: torch.Tensor) -> torch.Tensor:
+    """evaluation_utils.py:144-154: wrapped first difference, results may be negative."""
+    dqs = qpath[1:] - qpath[0:-1]
+    if isinstance(qpath, torch.Tensor):
+        return torch.remainder(dqs + torch.pi, 2 * torch.pi) - torch.pi
+    return np.remainder(dqs + np.pi, 2 * np.pi) - np.pi
+
+
+def prismatic_changes(x: torch.Tensor) -> torch.Tensor:
+    return x[1:] - x[0:-1]
+
+
+def calculate_mjac_deg(x: torch.Tensor) -> float:
+    return torch.rad2deg(angular_changes(x).abs().max()).item()
+
+
+def calculate_per_timestep_mjac_deg(x: torch.Tensor) -> torch.Tensor:
+    return torch.max(torch.rad2deg(angular_changes(x).abs()), dim=1).values
+
+
+def calculate_per_timestep_mjac_cm(x: torch.Tensor) -> torch.Tensor:
+    return 100 * torch.max(prismatic_changes(x).abs(), dim=1).values
+
+
+def get_mjacs(robot, qpath: torch.Tensor):
+    qps_revolute, qps_prismatic = robot.split_configs_to_revolute_and_prismatic(qpath)
+    if qps_prismatic.numel() > 0:
+        return calculate_mjac_deg(qps_revolute), calculate_per_timestep_mjac_cm(qps_prismatic).abs().max().item()
+    return calculate_mjac_deg(qps_revolute), 0.0
+
+
+def joint_limits_exceeded(robot_joint_limits: List[Tuple[float, float]], qs: np.ndarray):
+    """evaluation_utils.py:16-26"""
+    assert len(robot_joint_limits) == qs.shape[1]
+    n = qs.shape[0]
+    pcts = []
+    for i, (l, u) in enumerate(robot_joint_limits):
+        assert l < u
+        n_violating = (qs[:, i] < l).sum() + (u < qs[:, i]).sum()
+        pcts.append(100 * n_violating / n)
+    return any(vp > 0 for vp in pcts), pcts
+
+
+def errors_are_below_threshold(max_allowed_position_error_cm, max_allowed_rotation_error_deg, max_allowed_mjac_deg,
+                               max_allowed_mjac_cm, max_pos_cm: float, max_rot_deg: float, mjac_deg: float,
+                               mjac_cm: float):
+    """evaluation_utils.py:29-75 on already-reduced maxima (strict '<', as the reference)."""
+    pose_pos_valid = max_pos_cm < max_allowed_position_error_cm
+    pose_rot_valid = max_rot_deg < max_allowed_rotation_error_deg
+    mjac_rev_valid = mjac_deg < max_allowed_mjac_deg
+    mjac_pris_valid = mjac_cm < max_allowed_mjac_cm
+    return (pose_pos_valid and pose_rot_valid and mjac_rev_valid and mjac_pris_valid,
+            (pose_pos_valid, pose_rot_valid, mjac_rev_valid, mjac_pris_valid))

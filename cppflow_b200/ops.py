@@ -1,0 +1,246 @@
+"""Thin functional layer over the C ABI: allocates outputs with torch, checks shapes like the reference's
+asserts do, passes raw pointers + the current CUDA stream.  Everything here runs on the GPU; nothing falls back."""
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import LmParamsC, ptr, stream_ptr, require_cuda, check
+
+ROBOT_IDS = {"fetch": 0, "fetch_arm": 1, "panda": 2}
+
+
+def _info(robot_id: int) -> _lib.RobotInfoC:
+    info = _lib.RobotInfoC()
+    check(_lib.load().cppflow_robot_info_get(robot_id, info))
+    return info
+
+
+class Obstacles:
+    """Host-side copy of the cuboid tables of a Problem (obstacles_cuboids [6], obstacles_Tcuboids [4,4];
+    data_type_utils.py:109-127), flattened once so every launch can pass them by value."""
+
+    def __init__(self, cuboids: Optional[Sequence[torch.Tensor]] = None, Tcuboids: Optional[Sequence[torch.Tensor]] = None):
+        cuboids = list(cuboids) if cuboids is not None else []
+        Tcuboids = list(Tcuboids) if Tcuboids is not None else []
+        assert len(cuboids) == len(Tcuboids), "cuboids / Tcuboids length mismatch"
+        assert len(cuboids) <= 8, "at most 8 cuboid obstacles are supported"
+        self.n = len(cuboids)
+        cu, tc = [], []
+        for c, T in zip(cuboids, Tcuboids):
+            c = torch.as_tensor(c).detach().float().cpu().reshape(-1)
+            T = torch.as_tensor(T).detach().float().cpu()
+            assert c.numel() == 6 and T.shape == (4, 4)
+            cu += c.tolist()
+            tc += T.reshape(-1).tolist()
+        self._cu = _lib.host_floats(cu) if self.n else None
+        self._tc = _lib.host_floats(tc) if self.n else None
+
+    @property
+    def cuboids_ptr(self):
+        return self._cu
+
+    @property
+    def Tcuboids_ptr(self):
+        return self._tc
+
+    def single(self, i: int) -> "Obstacles":
+        o = Obstacles.__new__(Obstacles)
+        o.n = 1
+        o._cu = _lib.host_floats(list(self._cu[6 * i : 6 * i + 6]))
+        o._tc = _lib.host_floats(list(self._tc[16 * i : 16 * i + 16]))
+        return o
+
+
+NO_OBSTACLES = None
+
+
+def _obs(ob: Optional[Obstacles]):
+    if ob is None or ob.n == 0:
+        return None, None, 0
+    return ob.cuboids_ptr, ob.Tcuboids_ptr, ob.n
+
+
+def make_params(pms) -> LmParamsC:
+    """OptimizationParameters (lm_hyper_parameters.py:14-80) -> cppflow_lm_params.  None fields (the reference's
+    parameter sets leave unused alphas as None) become 0."""
+
+    def f(v):
+        return 0.0 if v is None else float(v)
+
+    for flag in ("pose_do_scale_down_satisfied", "differencing_do_ignore_satisfied", "differencing_do_scale_satisfied"):
+        if getattr(pms, flag, False):
+            raise NotImplementedError(
+                f"OptimizationParameters.{flag}=True is not used by the live parameter sets "
+                "(lm_hyper_parameters.py:86-151) and is not implemented by the CUDA path"
+            )
+    return LmParamsC(
+        f(pms.lm_lambda), f(pms.alpha_position), f(pms.alpha_rotation), f(pms.alpha_differencing),
+        f(pms.alpha_differencing_prismatic_scaling), f(pms.alpha_virtual_configs), f(pms.alpha_self_collision),
+        f(pms.alpha_env_collision), int(bool(pms.use_pose)), int(bool(pms.use_differencing)),
+        int(bool(pms.use_virtual_configs)), int(pms.n_virtual_configs or 0), int(bool(pms.use_self_collisions)),
+        int(bool(pms.use_env_collisions)),
+    )
+
+
+def _check_q(q: torch.Tensor, ndof: int, name="x") -> torch.Tensor:
+    q = require_cuda(q, name)
+    assert q.dim() == 2 and q.shape[1] == ndof, f"{name} must be [n, {ndof}], is {tuple(q.shape)}"
+    return q
+
+
+def forward_kinematics(rid: int, ndof: int, q: torch.Tensor) -> torch.Tensor:
+    q = _check_q(q, ndof)
+    out = torch.empty((q.shape[0], 7), device=q.device, dtype=torch.float32)
+    check(_lib.load().cppflow_forward_kinematics(rid, ptr(q), q.shape[0], ptr(out), stream_ptr(q.device)))
+    return out
+
+
+def jacobian(rid: int, ndof: int, q: torch.Tensor) -> torch.Tensor:
+    q = _check_q(q, ndof)
+    out = torch.empty((q.shape[0], 6, ndof), device=q.device, dtype=torch.float32)
+    check(_lib.load().cppflow_jacobian(rid, ptr(q), q.shape[0], ptr(out), stream_ptr(q.device)))
+    return out
+
+
+def pose_errors(rid: int, ndof: int, q: torch.Tensor, target: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    q = _check_q(q, ndof)
+    target = require_cuda(target, "target_poses")
+    assert target.dim() == 2 and target.shape[1] == 7 and target.shape[0] > 0
+    assert q.shape[0] % target.shape[0] == 0, "x rows must be a multiple of the target path length"
+    err = torch.empty((q.shape[0], 6), device=q.device, dtype=torch.float32)
+    cur = torch.empty((q.shape[0], 7), device=q.device, dtype=torch.float32)
+    check(_lib.load().cppflow_pose_errors(rid, ptr(q), ptr(target), q.shape[0], target.shape[0], ptr(err), ptr(cur),
+                                          stream_ptr(q.device)))
+    return err, cur
+
+
+def lm_pose_step(rid: int, ndof: int, params: LmParamsC, q: torch.Tensor, target: torch.Tensor, clamp: bool,
+                 return_residual: bool = False, out: Optional[torch.Tensor] = None):
+    q = _check_q(q, ndof)
+    target = require_cuda(target, "target_path")
+    assert target.dim() == 2 and target.shape[1] == 7 and target.shape[0] > 0
+    assert q.shape[0] % target.shape[0] == 0, "x rows must be a multiple of the target path length"
+    n = q.shape[0]
+    x_out = torch.empty_like(q) if out is None else out
+    J = torch.empty((n, 6, ndof), device=q.device, dtype=torch.float32) if return_residual else None
+    e = torch.empty((n, 6, 1), device=q.device, dtype=torch.float32) if return_residual else None
+    check(_lib.load().cppflow_lm_pose_step(rid, params, ptr(q), ptr(target), n, target.shape[0], int(clamp), ptr(x_out),
+                                           ptr(J), ptr(e), stream_ptr(q.device)))
+    if return_residual:
+        return x_out, J, e
+    return x_out
+
+
+def clamp_to_joint_limits_(rid: int, ndof: int, q: torch.Tensor) -> torch.Tensor:
+    assert q.is_cuda and q.dtype == torch.float32 and q.is_contiguous(), "in-place clamp needs a contiguous fp32 CUDA tensor"
+    assert q.dim() == 2 and q.shape[1] == ndof
+    check(_lib.load().cppflow_clamp_to_joint_limits(rid, ptr(q), q.shape[0], stream_ptr(q.device)))
+    return q
+
+
+def self_collision_distances(rid: int, ndof: int, n_pairs: int, q: torch.Tensor, with_jacobian: bool = False):
+    q = _check_q(q, ndof)
+    n = q.shape[0]
+    d = torch.empty((n, n_pairs), device=q.device, dtype=torch.float32)
+    J = torch.empty((n, n_pairs, ndof), device=q.device, dtype=torch.float32) if with_jacobian else None
+    check(_lib.load().cppflow_self_collision_distances(rid, ptr(q), n, ptr(d), ptr(J), stream_ptr(q.device)))
+    return (d, J) if with_jacobian else d
+
+
+def env_collision_distances(rid: int, ndof: int, n_caps: int, q: torch.Tensor, ob: Obstacles, index: int = 0,
+                            with_jacobian: bool = False):
+    q = _check_q(q, ndof)
+    n = q.shape[0]
+    one = ob if ob.n == 1 and index == 0 else ob.single(index)
+    d = torch.empty((n, n_caps), device=q.device, dtype=torch.float32)
+    J = torch.empty((n, n_caps, ndof), device=q.device, dtype=torch.float32) if with_jacobian else None
+    check(_lib.load().cppflow_env_collision_distances(rid, ptr(q), n, one.cuboids_ptr, one.Tcuboids_ptr, ptr(d), ptr(J),
+                                                      stream_ptr(q.device)))
+    return (d, J) if with_jacobian else d
+
+
+def collision_flags(rid: int, ndof: int, q: torch.Tensor, ob: Optional[Obstacles], want_self=True, want_env=True):
+    q = _check_q(q, ndof)
+    n = q.shape[0]
+    s = torch.empty((n,), device=q.device, dtype=torch.uint8) if want_self else None
+    e = torch.empty((n,), device=q.device, dtype=torch.uint8) if want_env else None
+    cu, tc, no = _obs(ob)
+    check(_lib.load().cppflow_collision_flags(rid, ptr(q), n, cu, tc, no, ptr(s), ptr(e), stream_ptr(q.device)))
+    return s, e
+
+
+_WORKSPACES = {}
+
+
+def _workspace(device, nbytes: int, key: str) -> torch.Tensor:
+    """Grow-only scratch buffer per (device, purpose): the C ABI never allocates."""
+    k = (str(device), key)
+    buf = _WORKSPACES.get(k)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty((max(nbytes, 256),), device=device, dtype=torch.uint8)
+        _WORKSPACES[k] = buf
+    return buf
+
+
+def lm_full_step(rid: int, ndof: int, params: LmParamsC, q: torch.Tensor, xv: Optional[torch.Tensor],
+                 target: Optional[torch.Tensor], P: int, T: int, ob: Optional[Obstacles], clamp: bool,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    q = _check_q(q, ndof)
+    assert q.shape[0] == P * T, f"x must have P*T = {P * T} rows, has {q.shape[0]}"
+    if xv is not None:
+        xv = _check_q(xv, ndof, "virtual_configs")
+        assert xv.shape == q.shape
+    if target is not None:
+        target = require_cuda(target, "target_path")
+        assert target.shape == (T, 7), f"target_path must be [{T}, 7], is {tuple(target.shape)}"
+    lib = _lib.load()
+    nbytes = lib.cppflow_lm_full_workspace_bytes(rid, P, T)
+    ws = _workspace(q.device, nbytes, "lm_full")
+    x_out = torch.empty_like(q) if out is None else out
+    cu, tc, no = _obs(ob)
+    check(lib.cppflow_lm_full_step(rid, params, ptr(q), ptr(xv), ptr(target), P, T, cu, tc, no, int(clamp), ptr(ws),
+                                   ws.numel(), ptr(x_out), stream_ptr(q.device)))
+    return x_out
+
+
+def joint_limit_flags(rid: int, ndof: int, q2d: torch.Tensor, eps_revolute: float, eps_prismatic: float) -> torch.Tensor:
+    q2d = _check_q(q2d, ndof, "qs")
+    out = torch.empty((q2d.shape[0],), device=q2d.device, dtype=torch.float32)
+    check(_lib.load().cppflow_joint_limit_flags(rid, ptr(q2d), q2d.shape[0], float(eps_revolute), float(eps_prismatic),
+                                                ptr(out), stream_ptr(q2d.device)))
+    return out
+
+
+def dp_search(rid: int, ndof: int, q: torch.Tensor, self_flags: torch.Tensor, env_flags: torch.Tensor):
+    """-> best_path [T,D], memo int32 [k,T], costs [k,T], chosen int32 [T]"""
+    q = require_cuda(q, "q")
+    assert q.dim() == 3 and q.shape[2] == ndof, f"q must be [k, T, {ndof}], is {tuple(q.shape)}"
+    k, T, _ = q.shape
+    sf = require_cuda(self_flags.to(q.device), "self_collision_violations", torch.uint8)
+    ef = require_cuda(env_flags.to(q.device), "env_collision_violations", torch.uint8)
+    assert sf.shape == (k, T) and ef.shape == (k, T)
+    lib = _lib.load()
+    ws = _workspace(q.device, lib.cppflow_dp_search_workspace_bytes(k, T), "dp_search")
+    best = torch.empty((T, ndof), device=q.device, dtype=torch.float32)
+    memo = torch.empty((k, T), device=q.device, dtype=torch.int32)
+    costs = torch.empty((k, T), device=q.device, dtype=torch.float32)
+    chosen = torch.empty((T,), device=q.device, dtype=torch.int32)
+    check(lib.cppflow_dp_search(rid, ptr(q), ptr(sf), ptr(ef), k, T, ptr(ws), ws.numel(), ptr(best), ptr(memo),
+                                ptr(costs), ptr(chosen), stream_ptr(q.device)))
+    return best, memo, costs, chosen
+
+
+METRIC_NAMES = ("max_pos_cm", "max_rot_deg", "mjac_deg", "mjac_cm", "tl", "min_self", "min_env")
+
+
+def path_metrics(rid: int, ndof: int, q: torch.Tensor, target: torch.Tensor, P: int, T: int,
+                 ob: Optional[Obstacles]) -> torch.Tensor:
+    q = _check_q(q, ndof)
+    assert q.shape[0] == P * T
+    target = require_cuda(target, "target_path")
+    assert target.shape == (T, 7)
+    out = torch.empty((P, 8), device=q.device, dtype=torch.float32)
+    cu, tc, no = _obs(ob)
+    check(_lib.load().cppflow_path_metrics(rid, ptr(q), ptr(target), P, T, cu, tc, no, ptr(out), stream_ptr(q.device)))
+    return out

@@ -1,0 +1,156 @@
+/* cppflow_b200 - C ABI of the B200-native path-refinement hot path of jstmn/cppflow.
+ *
+ * The reference is pure Python: it has no FFI.  Its boundary for this path is the Python call surface
+ * of cppflow/{search,collision_detection,optimization,optimization_utils}.py plus the jrl.Robot methods
+ * those modules call.  Each entry point below names the reference interface it
+ * replaces.  The Python host in cppflow_b200/ binds these with ctypes (see INTEGRATION.md for the stub a
+ * reference maintainer would add).
+ *
+ * Conventions
+ *  - every pointer named d_* is DEVICE memory (fp32 unless stated), contiguous, row-major;
+ *    h_* pointers are HOST memory read during the call (small tables, copied into the kernel parameters);
+ *  - `stream` is a cudaStream_t passed as void* (0 = default stream); calls are asynchronous on it;
+ *  - no entry point allocates device memory or synchronises: the caller supplies outputs and workspaces;
+ *  - return value: 0 on success, a negative CPPFLOW_E_* code otherwise (cppflow_last_error() has the text).
+ *  - robot ids: 0 = Fetch (8 dof, prismatic torso + 7 revolute), 1 = FetchArm (7 dof), 2 = Panda (7 dof)
+ *    (planners.py:34-41).
+ *  - poses are [x, y, z, qw, qx, qy, qz] (README.md:8); Jacobian rows are [wx wy wz vx vy vz]
+ *    (optimization.py:77-80).
+ */
+#ifndef CPPFLOW_B200_H
+#define CPPFLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPPFLOW_ROBOT_FETCH 0
+#define CPPFLOW_ROBOT_FETCH_ARM 1
+#define CPPFLOW_ROBOT_PANDA 2
+
+#define CPPFLOW_OK 0
+#define CPPFLOW_E_INVALID (-1)   /* bad argument (robot id, sizes, null pointer) */
+#define CPPFLOW_E_CUDA (-2)      /* a CUDA runtime call / launch failed */
+#define CPPFLOW_E_WORKSPACE (-3) /* workspace too small */
+
+#define CPPFLOW_MAX_DOF 8
+#define CPPFLOW_MAX_CAPSULES 10
+#define CPPFLOW_MAX_PAIRS 28
+#define CPPFLOW_MAX_OBSTACLES 8
+
+/* Mirrors the fields of OptimizationParameters the live parameter sets use
+ * (lm_hyper_parameters.py:14-80; ALT_LOSS_V2_1_DIFF :86-118, ALT_LOSS_V2_1_POSE :119-151). */
+typedef struct cppflow_lm_params {
+    float lm_lambda;
+    float alpha_position;
+    float alpha_rotation;
+    float alpha_differencing;
+    float alpha_differencing_prismatic_scaling;
+    float alpha_virtual_configs;
+    float alpha_self_collision;
+    float alpha_env_collision;
+    int32_t use_pose;
+    int32_t use_differencing;
+    int32_t use_virtual_configs;
+    int32_t n_virtual_configs;
+    int32_t use_self_collisions;
+    int32_t use_env_collisions;
+} cppflow_lm_params;
+
+/* Static description of a robot model (what the hot path reads from jrl.Robot: ndof, limits,
+ * prismatic idxs, capsule table, pair list - SURVEY.md 8b). */
+typedef struct cppflow_robot_info {
+    int32_t ndof;
+    int32_t n_capsules;
+    int32_t n_pairs;
+    int32_t n_chain;
+    float lower[CPPFLOW_MAX_DOF];
+    float upper[CPPFLOW_MAX_DOF];
+    int32_t is_prismatic[CPPFLOW_MAX_DOF];
+    float capsules[CPPFLOW_MAX_CAPSULES][7]; /* x1 y1 z1 x2 y2 z2 r, link frame */
+    int32_t capsule_frame[CPPFLOW_MAX_CAPSULES];
+    int32_t pairs[CPPFLOW_MAX_PAIRS][2];
+    char name[16];
+} cppflow_robot_info;
+
+const char* cppflow_version(void);
+const char* cppflow_last_error(void);
+
+/* jrl.Robot properties (ndof, actuated_joints_limits, prismatic_joint_idxs, _collision_capsules_by_link). */
+int cppflow_robot_info_get(int robot, cppflow_robot_info* out);
+
+/* Robot.forward_kinematics(x) -> [n,7]   (optimization_utils.py:811, evaluation_utils.py:115) */
+int cppflow_forward_kinematics(int robot, const float* d_q, int64_t n, float* d_poses, void* stream);
+
+/* Robot.jacobian(x) -> [n,6,ndof]   (optimization.py:74, optimization_utils.py:281) */
+int cppflow_jacobian(int robot, const float* d_q, int64_t n, float* d_J, void* stream);
+
+/* get_6d_pose_errors(robot, x, target_poses) -> ([n,6], [n,7])   (optimization_utils.py:802-820).
+ * target row of config i is i % n_targets (lets one [T,7] path serve P stacked paths). */
+int cppflow_pose_errors(int robot, const float* d_q, const float* d_target, int64_t n, int64_t n_targets,
+                        float* d_err, float* d_cur_poses, void* stream);
+
+/* levenberg_marquardt_only_pose + clamp_to_joint_limits   (optimization.py:61-92, optimization_utils.py:823-833).
+ * d_x_out = clamp(x + dx) when do_clamp, x + dx otherwise.  d_J_out [n,6,ndof] / d_e_out [n,6] (alpha-scaled,
+ * as returned with return_residual=True) may be NULL. */
+int cppflow_lm_pose_step(int robot, const cppflow_lm_params* params, const float* d_q, const float* d_target,
+                         int64_t n, int64_t n_targets, int do_clamp, float* d_x_out, float* d_J_out, float* d_e_out,
+                         void* stream);
+
+/* clamp_to_joint_limits(robot, x), in place   (optimization_utils.py:823-833) */
+int cppflow_clamp_to_joint_limits(int robot, float* d_q, int64_t n, void* stream);
+
+/* Robot.self_collision_distances(x) -> [n,S] and its Jacobian [n,S,ndof] (d_J may be NULL)
+ * (collision_detection.py:65, optimization_utils.py:652,670) */
+int cppflow_self_collision_distances(int robot, const float* d_q, int64_t n, float* d_dist, float* d_J, void* stream);
+
+/* Robot.env_collision_distances(x, cuboid, Tcuboid) -> [n,C] and its Jacobian [n,C,ndof] (d_J may be NULL)
+ * (collision_detection.py:40, optimization_utils.py:690,710).  h_cuboid[6] = lo,hi; h_Tcuboid[16] row-major 4x4
+ * (data_type_utils.py:109-127). */
+int cppflow_env_collision_distances(int robot, const float* d_q, int64_t n, const float* h_cuboid,
+                                    const float* h_Tcuboid, float* d_dist, float* d_J, void* stream);
+
+/* qpaths_batched_self_collisions / qpaths_batched_env_collisions (collision_detection.py:27-69):
+ * flags[i] = min over pairs/capsules (and obstacles) of the distance < 0.  Either output may be NULL.
+ * h_cuboids [n_obstacles,6], h_Tcuboids [n_obstacles,16]. */
+int cppflow_collision_flags(int robot, const float* d_q, int64_t n, const float* h_cuboids, const float* h_Tcuboids,
+                            int n_obstacles, uint8_t* d_self_flags, uint8_t* d_env_flags, void* stream);
+
+/* levenberg_marquardt_full (get_r_and_J + _lm_full_step) + clamp_to_joint_limits, for P independent paths of T
+ * waypoints (optimization.py:95-144, optimization_utils.py:486-731).  The normal equations are assembled
+ * implicitly as a symmetric block-tridiagonal system (ndof x ndof blocks) and solved by block Cholesky.
+ * d_xv = virtual configs [P,T,ndof] (NULL: equal to x, the run_lm_alternating_loss case, optimization.py:253).
+ * Workspace: cppflow_lm_full_workspace_bytes(robot, P, T) bytes of device memory. */
+size_t cppflow_lm_full_workspace_bytes(int robot, int64_t P, int64_t T);
+int cppflow_lm_full_step(int robot, const cppflow_lm_params* params, const float* d_q, const float* d_xv,
+                         const float* d_target, int64_t P, int64_t T, const float* h_cuboids, const float* h_Tcuboids,
+                         int n_obstacles, int do_clamp, void* d_workspace, size_t workspace_bytes, float* d_x_out,
+                         void* stream);
+
+/* joint_limit_almost_violations_3d(robot, qs, eps_revolute, eps_prismatic) -> float32 0/1 [n]  (search.py:25-52) */
+int cppflow_joint_limit_flags(int robot, const float* d_q, int64_t n, float eps_revolute, float eps_prismatic,
+                              float* d_flags, void* stream);
+
+/* dp_search (search.py:128-173): bottleneck DP over k candidate paths.
+ * in : d_q [k,T,ndof]; d_self_flags, d_env_flags uint8 [k,T]
+ * out: d_best_path [T,ndof]; d_memo int32 [k,T]; d_costs [k,T]; d_chosen int32 [T] (candidate index per waypoint)
+ * Workspace: cppflow_dp_search_workspace_bytes(k, T) bytes. */
+size_t cppflow_dp_search_workspace_bytes(int64_t k, int64_t T);
+int cppflow_dp_search(int robot, const float* d_q, const uint8_t* d_self_flags, const uint8_t* d_env_flags, int64_t k,
+                      int64_t T, void* d_workspace, size_t workspace_bytes, float* d_best_path, int32_t* d_memo,
+                      float* d_costs, int32_t* d_chosen, void* stream);
+
+/* Per-path validity metrics (x_is_valid without the klampt calls: optimization_utils.py:836-886,
+ * evaluation_utils.py:29-75,113-141; TL of optimization.py:173-175).  d_out [P,8] =
+ * {max position error cm, max rotation error deg, max |dq| revolute deg, max |dq| prismatic cm,
+ *  trajectory length rad, min capsule self distance m, min capsule env distance m (+inf if no obstacles), 0}. */
+int cppflow_path_metrics(int robot, const float* d_q, const float* d_target, int64_t P, int64_t T,
+                         const float* h_cuboids, const float* h_Tcuboids, int n_obstacles, float* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPPFLOW_B200_H */

@@ -1,0 +1,217 @@
+"""GPU parity: every C-ABI entry point (through the Python host, which only forwards pointers) against the CPU
+oracle on seeded inputs, and against the golden vectors produced by the real reference code.
+
+Tolerances (BASELINE.json north_star): FK positions 1e-5 m, rotations 1e-5 rad, LM-refined joints 1e-4 rad;
+dp_search back-pointers and collision booleans bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import robots as R, kinematics as K, geometry as G, lm as L, search as S
+from tests.helpers import OBSTACLES, cuboid_tensors, random_configs, synthetic_problem
+
+pytestmark = pytest.mark.gpu
+ROBOTS = ["fetch", "fetch_arm", "panda"]
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def robots():
+    from cppflow_b200.robot import get_robot
+
+    return {r: get_robot(r) for r in ROBOTS}
+
+
+def quat_align(q, ref):
+    s = torch.sign((q * ref).sum(dim=1, keepdim=True))
+    s[s == 0] = 1
+    return q * s
+
+
+@pytest.mark.parametrize("r", ROBOTS)
+def test_fk_and_jacobian(robots, r):
+    m = R.get_model(r)
+    x = random_configs(m, 20000, seed=1)
+    pose = robots[r].forward_kinematics(x.to(DEV)).cpu()
+    ref = K.forward_kinematics(m, x.double())
+    assert (pose[:, :3].double() - ref[:, :3]).abs().max() < 1e-5
+    assert (quat_align(pose[:, 3:].double(), ref[:, 3:]) - ref[:, 3:]).abs().max() < 1e-5
+    J = robots[r].jacobian(x.to(DEV)).cpu()
+    assert (J.double() - K.jacobian(m, x.double())).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("r", ROBOTS)
+def test_pose_errors(robots, r):
+    from cppflow_b200.optimization_utils import get_6d_pose_errors
+
+    m, target, x0 = synthetic_problem(r, 4, 64, seed=2)
+    e, cur = get_6d_pose_errors(robots[r], x0.to(DEV), target.repeat(4, 1).to(DEV))
+    e_ref, cur_ref = L.get_6d_pose_errors(m, x0.double(), target.repeat(4, 1).double())
+    assert e.shape == (256, 6, 1)
+    assert (e.cpu().double() - e_ref).abs().max() < 1e-5
+    assert (cur.cpu()[:, :3].double() - cur_ref[:, :3]).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("r", ROBOTS)
+def test_collision_distances_and_jacobians(robots, r):
+    m = R.get_model(r)
+    x = random_configs(m, 5000, seed=3)
+    d = robots[r].self_collision_distances(x.to(DEV)).cpu()
+    d_ref, J_ref = G.self_collision_distances(m, x.double(), with_jacobian=True)
+    assert d.shape == d_ref.shape
+    assert (d.double() - d_ref).abs().max() < 1e-5
+    J = robots[r].self_collision_distances_jacobian(x.to(DEV)).cpu()
+    assert (J.double() - J_ref).abs().max() < 2e-4
+    cuboids, Tcuboids = cuboid_tensors(OBSTACLES[r])
+    for c, Tc in zip(cuboids, Tcuboids):
+        d = robots[r].env_collision_distances(x.to(DEV), c.to(DEV), Tc.to(DEV)).cpu()
+        d_ref, J_ref = G.env_collision_distances(m, x.double(), c, Tc, with_jacobian=True)
+        assert (d.double() - d_ref).abs().max() < 1e-5
+        J = robots[r].env_collision_distances_jacobian(x.to(DEV), c, Tc).cpu()
+        # the gradient is discontinuous where the closest point switches feature: compare where it is well defined
+        ok = (d_ref.abs() > 1e-4)
+        assert ((J.double() - J_ref).abs().amax(dim=2)[ok] < 2e-3).float().mean() > 0.999
+
+
+def test_rotated_cuboid(robots):
+    m = R.get_model("panda")
+    x = random_configs(m, 2000, seed=5)
+    c = torch.tensor([-0.1, -0.2, -0.15, 0.1, 0.2, 0.15])
+    Tc = torch.eye(4)
+    ang = 0.7
+    Tc[:3, :3] = torch.tensor([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1.0]])
+    Tc[:3, 3] = torch.tensor([0.3, 0.1, 0.5])
+    d = robots["panda"].env_collision_distances(x.to(DEV), c, Tc).cpu()
+    d_ref = G.env_collision_distances(m, x.double(), c, Tc.double())
+    assert (d.double() - d_ref).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("r", ROBOTS)
+def test_collision_flags_bit_exact(robots, r, golden):
+    from cppflow_b200.collision_detection import qpaths_batched_self_collisions, qpaths_batched_env_collisions
+    from cppflow_b200.data_types import Problem, Constraints
+
+    m = R.get_model(r)
+    cuboids, Tcuboids = cuboid_tensors(OBSTACLES[r])
+    k, T = 40, 128
+    q = random_configs(m, k * T, seed=4).reshape(k, T, m.ndof)
+    target = K.forward_kinematics(m, q[0].double()).float()
+    problem = Problem(Constraints(0.01, 0.1, 7.0, 2.0), target.to(DEV), None, robots[r], "t", "t", [], Tcuboids, cuboids, [])
+    s = qpaths_batched_self_collisions(problem, q.to(DEV)).cpu()
+    e = qpaths_batched_env_collisions(problem, q.to(DEV)).cpu()
+    assert s.dtype == torch.bool and s.shape == (k, T)
+    # oracle in fp32 (the reference's dtype); booleans must agree wherever |min distance| > 1e-6 m
+    q2 = q.reshape(-1, m.ndof)
+    ds = G.self_collision_distances(m, q2).min(dim=1).values.reshape(k, T)
+    band = ds.abs() > 1e-6
+    assert torch.equal(s[band], (ds < 0)[band]) and band.float().mean() > 0.9999
+    de = torch.stack([G.env_collision_distances(m, q2, c, Tc).min(dim=1).values for c, Tc in zip(cuboids, Tcuboids)]).min(dim=0).values.reshape(k, T)
+    band = de.abs() > 1e-6
+    assert torch.equal(e[band], (de < 0)[band]) and band.float().mean() > 0.9999
+    assert s.any() and e.any() and not s.all() and not e.all()
+    # golden vectors from the real reference
+    gq = torch.tensor(golden[f"{r}/cd/q"])
+    gc, gT = [torch.tensor(c) for c in golden[f"{r}/lm/cuboids"]], [torch.tensor(t) for t in golden[f"{r}/lm/Tcuboids"]]
+    problem = Problem(Constraints(0.01, 0.1, 7.0, 2.0), target.to(DEV), None, robots[r], "t", "t", [], gT, gc, [])
+    assert np.array_equal(qpaths_batched_self_collisions(problem, gq.to(DEV)).cpu().numpy(), golden[f"{r}/cd/self"])
+    assert np.array_equal(qpaths_batched_env_collisions(problem, gq.to(DEV)).cpu().numpy(), golden[f"{r}/cd/env"])
+
+
+@pytest.mark.parametrize("r", ROBOTS)
+def test_dp_search_bit_exact(robots, r, golden):
+    from cppflow_b200 import ops
+    from cppflow_b200.search import dp_search, joint_limit_almost_violations_3d
+
+    m = R.get_model(r)
+    rob = robots[r]
+    # golden (real reference)
+    q = torch.tensor(golden[f"{r}/dp/q"])
+    sv, ev = torch.tensor(golden[f"{r}/dp/self_v"]), torch.tensor(golden[f"{r}/dp/env_v"])
+    best, memo, costs, chosen = ops.dp_search(rob.robot_id, rob.ndof, q.to(DEV), sv.to(DEV), ev.to(DEV))
+    assert np.array_equal(memo.cpu().numpy(), golden[f"{r}/dp/memo"])
+    assert np.array_equal(costs.cpu().numpy(), golden[f"{r}/dp/costs"])
+    assert np.array_equal(best.cpu().numpy(), golden[f"{r}/dp/best_path"])
+    assert np.array_equal(joint_limit_almost_violations_3d(rob, q.to(DEV)).cpu().numpy(), golden[f"{r}/dp/jlim"])
+    # seeded random case with 2 pi wraps, ties and k not a multiple of 32
+    for (k, T, seed) in [(37, 50, 0), (175, 60, 1), (1, 5, 2), (33, 1, 3)]:
+        g = torch.Generator().manual_seed(seed)
+        base = random_configs(m, T, seed=seed + 10)
+        q = base[None] + 0.4 * torch.randn((k, T, m.ndof), generator=g)
+        q[:, :, -1] += (torch.rand((k, T), generator=g) < 0.1).float() * 2 * np.pi
+        if k > 4:
+            q[3] = q[1]  # exact ties
+        sv = torch.rand((k, T), generator=g) < 0.2
+        ev = torch.rand((k, T), generator=g) < 0.2
+        ref_best, ref_memo, ref_costs, ref_chosen = S.dp_search(m, q, sv, ev)
+        out = dp_search(rob, q.to(DEV), sv.to(DEV), ev.to(DEV), verbosity=0)
+        best, memo, costs, chosen = ops.dp_search(rob.robot_id, rob.ndof, q.to(DEV), sv.to(DEV), ev.to(DEV))
+        assert torch.equal(memo.cpu(), ref_memo), (k, T)
+        assert torch.equal(costs.cpu(), ref_costs)
+        assert torch.equal(chosen.cpu().long(), ref_chosen)
+        assert torch.equal(best.cpu(), ref_best) and torch.equal(out.cpu(), ref_best)
+
+
+@pytest.mark.parametrize("r", ROBOTS)
+def test_pose_step(robots, r, golden):
+    from cppflow_b200 import ops
+    from cppflow_b200.lm_hyper_parameters import ALT_LOSS_V2_1_POSE
+
+    m, target, x0 = synthetic_problem(r, 16, 100, seed=6)
+    rob = robots[r]
+    prm = ops.make_params(ALT_LOSS_V2_1_POSE)
+    xn, J, e = ops.lm_pose_step(rob.robot_id, rob.ndof, prm, x0.to(DEV), target.to(DEV), clamp=False, return_residual=True)
+    x64, J64, e64 = L.levenberg_marquardt_only_pose(m, x0.double(), target.repeat(16, 1).double(), L.ALT_LOSS_V2_1_POSE, True)
+    assert (J.cpu().double() - J64).abs().max() < 5e-5
+    assert (e.cpu().double() - e64).abs().max() < 5e-5
+    err = (xn.cpu().double() - x64).abs().max(dim=1).values
+    assert err.max() < 1e-4, err.max()
+    # the reference's own fp32 step is much further from exact arithmetic than the kernel is
+    x32 = L.levenberg_marquardt_only_pose(m, x0, target.repeat(16, 1), L.ALT_LOSS_V2_1_POSE)
+    assert err.max() < (x32.double() - x64).abs().max()
+    # golden J / e from the real reference
+    gx, gt = torch.tensor(golden[f"{r}/lm/x"]), torch.tensor(golden[f"{r}/lm/target"])
+    xn, J, e = ops.lm_pose_step(rob.robot_id, rob.ndof, prm, gx.to(DEV), gt.to(DEV), clamp=False, return_residual=True)
+    np.testing.assert_allclose(J.cpu().numpy(), golden[f"{r}/lm/pose_step_J"], atol=2e-5)
+    np.testing.assert_allclose(e.cpu().numpy(), golden[f"{r}/lm/pose_step_e"], atol=2e-5)
+
+
+@pytest.mark.parametrize("r", ROBOTS)
+@pytest.mark.parametrize("mode", ["diff", "all"])
+def test_full_step_vs_dense_oracle(robots, r, mode):
+    from cppflow_b200 import ops
+    from cppflow_b200.lm_hyper_parameters import ALT_LOSS_V2_1_DIFF, ALT_LOSS_V2_1_POSE, OptimizationParameters
+
+    P, T = 3, 40
+    m, target, x0 = synthetic_problem(r, P, T, seed=7)
+    rob = robots[r]
+    # make collisions fire: pull a few waypoints of each path towards colliding configurations
+    cand = random_configs(m, 6000, seed=8)
+    cuboids, Tcuboids = cuboid_tensors(OBSTACLES[r])
+    bad_self = cand[G.self_collision_distances(m, cand).min(dim=1).values < -0.01]
+    bad_env = cand[G.env_collision_distances(m, cand, cuboids[0], Tcuboids[0]).min(dim=1).values < -0.01]
+    x0 = x0.reshape(P, T, -1).clone()
+    x0[:, 5] = bad_self[:P]
+    x0[:, 17] = bad_env[:P]
+    x0[:, 18] = bad_env[P : 2 * P]
+    x0 = x0.reshape(P * T, -1)
+    pms = OptimizationParameters(**ALT_LOSS_V2_1_DIFF.__dict__)
+    opms = L.LmParams()
+    if mode == "all":
+        pms.use_pose, pms.alpha_position, pms.alpha_rotation = True, ALT_LOSS_V2_1_POSE.alpha_position, ALT_LOSS_V2_1_POSE.alpha_rotation
+        opms = L.LmParams(use_pose=True)
+    xv = x0 + 0.01 * torch.randn(x0.shape, generator=torch.Generator().manual_seed(9))
+    ob = ops.Obstacles(cuboids, Tcuboids)
+    out = ops.lm_full_step(rob.robot_id, rob.ndof, ops.make_params(pms), x0.to(DEV), xv.to(DEV), target.to(DEV), P, T, ob,
+                           clamp=False).cpu()
+    n_active = 0
+    for p in range(P):
+        xp = x0[p * T : (p + 1) * T].double()
+        opms.virtual_configs = xv[p * T : (p + 1) * T].double()
+        Jd, rd = L.get_r_and_J(opms, m, xp, target.double(), Tcuboids, cuboids)
+        n_active += (0 if rd["self_collisions"] is None else rd["self_collisions"].shape[0])
+        n_active += (0 if rd["env_collisions"] is None else rd["env_collisions"].shape[0])
+        ref = L.lm_full_step(L.stack_rows(Jd), L.stack_rows(rd), xp, opms.lm_lambda)
+        err = (out[p * T : (p + 1) * T].double() - ref).abs().max()
+        step = (ref - xp).abs().max()
+        assert err < (1e-4 if mode == "diff" else 2e-3), (mode, p, float(err), float(step))
+    assert n_active > 0

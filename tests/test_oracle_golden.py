@@ -1,0 +1,214 @@
+"""CPU: the oracle restatement against vectors produced by the REAL reference code
+(tests/golden/make_golden.py) and against the known-answer vectors of the reference's own tests."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import robots as R, kinematics as K, geometry as G, lm as L, search as S
+from oracle.math_utils import geodesic_distance_between_quaternions
+
+ROBOTS = ["fetch", "fetch_arm", "panda"]
+
+
+def T(a, dtype=torch.float32):
+    return torch.tensor(np.asarray(a), dtype=dtype)
+
+
+def cub(golden, r):
+    c, t = golden[f"{r}/lm/cuboids"], golden[f"{r}/lm/Tcuboids"]
+    return [T(x) for x in t], [T(x) for x in c]
+
+
+@pytest.mark.parametrize("r", ROBOTS)
+def test_dp_search_bit_exact(golden, r):
+    m = R.get_model(r)
+    q = T(golden[f"{r}/dp/q"])
+    best, memo, costs, _ = S.dp_search(m, q, torch.tensor(golden[f"{r}/dp/self_v"]), torch.tensor(golden[f"{r}/dp/env_v"]))
+    assert np.array_equal(memo.numpy(), golden[f"{r}/dp/memo"])
+    assert np.array_equal(costs.numpy(), golden[f"{r}/dp/costs"])
+    assert np.array_equal(best.numpy(), golden[f"{r}/dp/best_path"])
+    assert np.array_equal(S.get_mjacs(q, m).numpy(), golden[f"{r}/dp/mjacs"])
+    assert np.array_equal(S.joint_limit_almost_violations_3d(m, q).numpy(), golden[f"{r}/dp/jlim"])
+
+
+@pytest.mark.parametrize("r", ["fetch_arm", "panda"])
+def test_dp_search_matches_slow_variant(golden, r):
+    # search.py:55-97 is a second implementation (without the prismatic x5): equal for all-revolute robots
+    m = R.get_model(r)
+    q = T(golden[f"{r}/dp/q"])
+    sv, ev = torch.tensor(golden[f"{r}/dp/self_v"]), torch.tensor(golden[f"{r}/dp/env_v"])
+    assert torch.equal(S.dp_search(m, q, sv, ev)[0], S.dp_search_slow(m, q, sv, ev))
+
+
+@pytest.mark.parametrize("r", ROBOTS)
+def test_pose_error_and_pose_step(golden, r):
+    m = R.get_model(r)
+    x, tgt = T(golden[f"{r}/lm/x"]), T(golden[f"{r}/lm/target"])
+    e, cur = L.get_6d_pose_errors(m, x, tgt)
+    np.testing.assert_allclose(e.numpy(), golden[f"{r}/lm/pose_err"], atol=1e-6)
+    np.testing.assert_allclose(cur.numpy(), golden[f"{r}/lm/cur_pose"], atol=1e-6)
+    xn, J, e = L.levenberg_marquardt_only_pose(m, x, tgt, L.ALT_LOSS_V2_1_POSE, return_residual=True)
+    np.testing.assert_allclose(J.numpy(), golden[f"{r}/lm/pose_step_J"], atol=1e-6)
+    np.testing.assert_allclose(e.numpy(), golden[f"{r}/lm/pose_step_e"], atol=1e-6)
+    np.testing.assert_allclose(xn.numpy(), golden[f"{r}/lm/pose_step_x"], atol=2e-4)
+
+
+@pytest.mark.parametrize("r", ROBOTS)
+def test_differencing_step(golden, r):
+    m = R.get_model(r)
+    x, tgt = T(golden[f"{r}/lm/x"]), T(golden[f"{r}/lm/target"])
+    Tc, c = cub(golden, r)
+    pms = L.LmParams(virtual_configs=x.clone())
+    Jd, rd = L.get_r_and_J(pms, m, x, tgt, Tc, c)
+    J, rr = L.stack_rows(Jd), L.stack_rows(rd)
+    assert J.shape == golden[f"{r}/lm/diff_step_J"].shape
+    np.testing.assert_allclose(J.numpy(), golden[f"{r}/lm/diff_step_J"], atol=1e-7)
+    np.testing.assert_allclose(rr.numpy(), golden[f"{r}/lm/diff_step_r"], atol=1e-7)
+    xn = L.lm_full_step(J, rr, x, pms.lm_lambda)
+    np.testing.assert_allclose(xn.numpy(), golden[f"{r}/lm/diff_step_x"], atol=1e-5)
+
+
+@pytest.mark.parametrize("r", ROBOTS)
+def test_all_terms_r_and_J(golden, r):
+    m = R.get_model(r)
+    x, xv, tgt = T(golden[f"{r}/lm/all_x"]), T(golden[f"{r}/lm/all_xv"]), T(golden[f"{r}/lm/target"])
+    Tc, c = cub(golden, r)
+    pms = L.LmParams(use_pose=True, virtual_configs=xv)
+    Jd, rd = L.get_r_and_J(pms, m, x, tgt, Tc, c)
+    assert rd["self_collisions"].shape[0] == int(golden[f"{r}/lm/all_n_self"]) > 0
+    assert rd["env_collisions"].shape[0] == int(golden[f"{r}/lm/all_n_env"]) > 0
+    J, rr = L.stack_rows(Jd), L.stack_rows(rd)
+    np.testing.assert_allclose(J.numpy(), golden[f"{r}/lm/all_J"], atol=2e-6)
+    np.testing.assert_allclose(rr.numpy(), golden[f"{r}/lm/all_r"], atol=2e-6)
+    xn = L.lm_full_step(J, rr, x, pms.lm_lambda)
+    np.testing.assert_allclose(xn.numpy(), golden[f"{r}/lm/all_step_x"], atol=5e-3)
+
+
+@pytest.mark.parametrize("r", ROBOTS)
+def test_collision_flags_and_metrics(golden, r):
+    m = R.get_model(r)
+    q = T(golden[f"{r}/cd/q"])
+    Tc, c = cub(golden, r)
+    assert np.array_equal(S.qpaths_batched_self_collisions(m, q).numpy(), golden[f"{r}/cd/self"])
+    assert np.array_equal(S.qpaths_batched_env_collisions(m, q, c, Tc).numpy(), golden[f"{r}/cd/env"])
+    assert golden[f"{r}/cd/self"].any() and golden[f"{r}/cd/env"].any()
+    x, tgt = T(golden[f"{r}/lm/x"]), T(golden[f"{r}/lm/target"])
+    ecm, edeg = L.calculate_pose_error_cm_deg(m, x, tgt)
+    np.testing.assert_allclose(ecm.numpy(), golden[f"{r}/ev/err_cm"], atol=1e-5)
+    np.testing.assert_allclose(edeg.numpy(), golden[f"{r}/ev/err_deg"], atol=1e-4)
+    np.testing.assert_array_equal(L.angular_changes(x).numpy(), golden[f"{r}/ev/angular_changes"])
+    np.testing.assert_array_equal(L.clamp_to_joint_limits(m, T(golden[f"{r}/lm/clamp_in"])).numpy(),
+                                  golden[f"{r}/lm/clamp_out"])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# known-answer vectors held by the reference's own tests
+
+
+def test_angular_changes_known_answers():
+    """tests/evaluation_utils_test.py:17-124"""
+    P2 = 2 * math.pi
+    cases = [
+        ([[0, 0, 0], [0, 0, 0], [0, 0, 0]], [[0, 0, 0], [0, 0, 0]]),
+        ([[0, 0, 0], [0, 0, 0], [0, 0, 0.1]], [[0, 0, 0], [0, 0, 0.1]]),
+        ([[0, 0, 0], [0, 0, 0.1], [0, 0, -0.1]], [[0, 0, 0.1], [0, 0, -0.2]]),
+        ([[0, -0.05, 0], [0, 0, 0.1], [0, 0, -0.1]], [[0, 0.05, 0.1], [0, 0, -0.2]]),
+        ([[0, 0, 0], [0, 0, P2 - 0.1], [0, 0, 0]], [[0, 0, -0.1], [0, 0, 0.1]]),
+        ([[0, 0, 0], [0, 0, P2 - 0.1], [-0.5, 0, 0.2]], [[0, 0, -0.1], [-0.5, 0, 0.3]]),
+    ]
+    for qpath, expected in cases:
+        torch.testing.assert_close(T(expected), L.angular_changes(T(qpath)))
+
+
+def test_joint_limit_almost_violations_known_answer():
+    """tests/search_test.py:22-57 (Fetch limits spelled out at :35-42)"""
+    m = R.get_model("fetch")
+    assert m.actuated_joints_limits == [(0, 0.38615), (-1.6056, 1.6056), (-1.221, 1.518), (-math.pi, math.pi),
+                                        (-2.251, 2.251), (-math.pi, math.pi), (-2.16, 2.16), (-math.pi, math.pi)]
+    qs = torch.zeros((2, 3, 8))
+    qs[0, 0] = T([0.051, 0, 0, 0, 0, 0, 0, 0])
+    qs[0, 1] = T([0.38615 - 0.001, 0, 0, 0, 0, 0, 0, 0])
+    qs[0, 2] = T([0.38615 - 0.051, 0, 0, 0, 0, 0, 0, 0])
+    qs[1, 0] = T([0.38615 - 0.051, 0, 0, -np.pi, 0, 0, 0, 0])
+    qs[1, 1] = T([0.38615 - 0.051, 0, 0, -np.pi + 0.11, 0, 0, 0, 0])
+    qs[1, 2] = T([0.38615 - 0.051, 0, 0, -np.pi + 0.11, 0, 0, 0, np.pi - 0.25])
+    expected = T([[0, 1, 0], [1, 0, 0]])
+    torch.testing.assert_close(S.joint_limit_almost_violations_3d(m, qs, eps_revolute=0.1, eps_prismatic=0.05), expected)
+
+
+def test_row_conventions():
+    """tests/optimization_utils_test.py:67-119: Fetch prismatic idx 0, Panda all revolute."""
+    assert R.get_model("fetch").prismatic_joint_idxs == [0]
+    assert R.get_model("panda").prismatic_joint_idxs == []
+    assert R.get_model("fetch_arm").ndof == 7 and R.get_model("fetch_arm").prismatic_joint_idxs == []
+
+
+def test_fetch_torso_moves_ee_z_only():
+    """tests/optimization_utils_test.py:377-402: moving joint 0 by d changes EE z by d, no rotation."""
+    m = R.get_model("fetch")
+    x = torch.zeros((1, 8), dtype=torch.float64)
+    x[0, 1:] = T([0.3, -0.2, 0.5, 1.0, -0.4, 0.6, 0.1], torch.float64)
+    x2 = x.clone()
+    x2[0, 0] += 0.1
+    p1, p2 = K.forward_kinematics(m, x), K.forward_kinematics(m, x2)
+    torch.testing.assert_close(p2[:, :3] - p1[:, :3], T([[0, 0, 0.1]], torch.float64))
+    torch.testing.assert_close(p2[:, 3:], p1[:, 3:])
+    # and the pose residual is alpha_position * delta on the z row, zero rotation (row order [rot x3, pos x3])
+    e, _ = L.get_6d_pose_errors(m, x, p2)
+    torch.testing.assert_close(e[0, :, 0], T([0, 0, 0, 0, 0, 0.1], torch.float64), atol=1e-12, rtol=0)
+
+
+def test_panda_fk_known_point():
+    """tests/planners_test.py:282-309: q0 -> [0.45, 0.5422, 0.7885 | 1,0,0,0] within 1e-3."""
+    m = R.get_model("panda")
+    q0 = T([[1.267967, 0.711829, -0.811080, -0.810924, -2.637594, 1.767759, 0.083284]], torch.float64)
+    pose = K.forward_kinematics(m, q0)[0]
+    np.testing.assert_allclose(pose[:3].numpy(), [0.45, 0.5421984559194368, 0.7885155964931997], atol=1e-3)
+    np.testing.assert_allclose(pose[3:].numpy(), [1, 0, 0, 0], atol=1e-3)
+
+
+def test_differencing_residual_is_row_major_delta():
+    """tests/optimization_utils_test.py:590-637"""
+    m = R.get_model("panda")
+    x = torch.arange(21, dtype=torch.float32).reshape(3, 7) * 0.01
+    _, r = L.get_r_and_J(L.LmParams(use_virtual_configs=False, use_self_collisions=False, use_env_collisions=False,
+                                    alpha_differencing=1.0), m, x, None)
+    torch.testing.assert_close(r["differencing"][:, 0], (x[1:] - x[:-1]).reshape(-1))
+
+
+@pytest.mark.parametrize("r", ROBOTS)
+def test_batched_pose_lm_equals_dense_lm(golden, r):
+    """tests/optimization_test.py:74-100: batched pose step == dense full step on pose-only params
+    (J, r atol 1e-5; x atol 5e-3)."""
+    m = R.get_model(r)
+    x, tgt = T(golden[f"{r}/lm/x"]), T(golden[f"{r}/lm/target"])
+    xb, Jb, eb = L.levenberg_marquardt_only_pose(m, x, tgt, L.ALT_LOSS_V2_1_POSE, return_residual=True)
+    Jd, rd = L.get_r_and_J(L.ALT_LOSS_V2_1_POSE, m, x, tgt)
+    n, D = x.shape
+    for i in range(n):
+        torch.testing.assert_close(Jd["pose"][6 * i : 6 * i + 6, D * i : D * i + D], Jb[i], atol=1e-5, rtol=0)
+    torch.testing.assert_close(rd["pose"].reshape(n, 6, 1), eb, atol=1e-5, rtol=0)
+    xd = L.lm_full_step(L.stack_rows(Jd), L.stack_rows(rd), x, 1e-6)
+    torch.testing.assert_close(xd, xb, atol=5e-3, rtol=0)
+
+
+def test_batched_equals_per_path_collision_flags(golden):
+    """tests/collision_checking_test.py:43-56"""
+    m = R.get_model("panda")
+    q = T(golden["panda/cd/q"])
+    Tc, c = cub(golden, "panda")
+    b_self = S.qpaths_batched_self_collisions(m, q)
+    b_env = S.qpaths_batched_env_collisions(m, q, c, Tc)
+    for i in range(q.shape[0]):
+        assert torch.equal(b_self[i], G.self_collision_distances(m, q[i]).min(dim=1).values < 0)
+        e = torch.zeros(q.shape[1], dtype=torch.bool)
+        for ci, Ti in zip(c, Tc):
+            e |= G.env_collision_distances(m, q[i], ci, Ti).min(dim=1).values < 0
+        assert torch.equal(b_env[i], e)
+
+
+def test_geodesic_floor():
+    q = T([[1.0, 0, 0, 0]])
+    assert abs(geodesic_distance_between_quaternions(q, q).item() - 2 * math.acos(1 - 1e-7)) < 1e-6
