@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""Benchmark of the path-refinement hot path (BASELINE.json metric: waypoint FK+Jac+collision+LM evals/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config 5): synthetic P = 8192 candidate paths x T = 300 waypoints of the 8-dof Fetch, the four
+fetch__circle cuboids as obstacles, seeds = smooth joint path + N(0, 0.05^2).  One "step" = ONE fused LM iteration
+with every residual term on (pose + joint differencing + virtual configs + capsule self- and env-collisions) followed
+by clamp_to_joint_limits, over all P*T waypoints; one waypoint evaluation = FK + 6xD Jacobian + 28 capsule-pair and
+40 capsule-cuboid distances + its share of the block-tridiagonal normal-equation assembly and solve.
+Multi-GPU: weak scaling - every rank refines its own shard of P paths, no collective in the data path; after the
+timed steps the per-path costs are all-gathered over NCCL and the argmin taken (inside the timed region).
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+# algorithmic FLOPs per waypoint evaluation (SURVEY.md 8d formula, Fetch instance; DESIGN.md "Roofline")
+F_ASSEMBLE = 581 + 96 + 90 + 624 + 2520 + 4800 + 63  # FK, Jacobian, pose error, normal equations, self, env, extra frames
+F_SOLVE = 1451                                       # block-tridiagonal factor/solve share: (7/3) D^3 + 4 D^2
+F_STEP_SURVEY = 9100                                 # the per-eval figure SURVEY.md 8d quotes for the fused iteration
+BYTES_PER_EVAL = 64                                  # read q once, write x_new once (8 dof * 4 B * 2)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--paths", type=int, default=8192)
+    ap.add_argument("--waypoints", type=int, default=300)
+    ap.add_argument("--cpu-sample-paths", type=int, default=24)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._halt = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=1.0)
+        return {
+            "sm_mhz": statistics.median(self.samples) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the reference's dense torch path on the host cores
+
+
+def cpu_reference_step_rate(T: int, sample_paths: int, steps: int, warmup: int):
+    """evals/s of the reference's CPU path (oracle/ port; the reference itself needs jrl and cannot be imported):
+    per path, dense LmResidualFns.get_r_and_J with every term on + _lm_full_step (dense (T*D)^2 Cholesky) + clamp."""
+    from oracle import robots as OR, lm as OL
+    from tests.helpers import synthetic_problem as oracle_problem, cuboid_tensors, FETCH_CIRCLE_OBSTACLES
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model, target, x0 = oracle_problem("fetch", sample_paths, T, seed=0)
+    cuboids, Tcuboids = cuboid_tensors(FETCH_CIRCLE_OBSTACLES)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        OL.run_fixed_schedule(model, x0, target, "a", Tcuboids, cuboids)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    mean_dt = sum(times) / len(times)
+    return sample_paths * T / mean_dt, mean_dt, cores
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warmup = 1 if args.warmup > 0 else 0
+    rate, dt, cores = cpu_reference_step_rate(args.waypoints, args.cpu_sample_paths, steps, warmup)
+    sample = (f"{args.cpu_sample_paths} of {args.paths} paths x {args.waypoints} waypoints per step (dense get_r_and_J + "
+              f"_lm_full_step, all terms on), fp32, torch {torch.__version__}, {cores} threads; evals/s is size-independent "
+              f"per path so the sample rate is the full-workload rate")
+    line = {
+        "impl": "reference",
+        "metric": "waypoint FK+Jac+collision+LM evals/s",
+        "value": rate,
+        "unit": "waypoint-evals/s",
+        "n_gpus": args.gpus,
+        "steps": steps,
+        "warmup": warmup,
+        "ms_per_step": dt * 1e3,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": rate, "unit": "waypoint-evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "waypoint-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": f"synthetic {args.paths} paths x {args.waypoints} waypoints Fetch 8-DOF, one fused LM iteration "
+                    "(pose + differencing + virtual configs + self/env capsule collisions) + clamp; 4 fetch__circle cuboids",
+        "paths_per_gpu": args.paths,
+        "waypoints": args.waypoints,
+        "robot": "fetch",
+        "parallelism": f"paths sharded over {n_gpus} GPU(s), no data-path collective",
+        "l2": "no flush: each step streams ~1.9 GB (q, x_new, 433 MB block workspace written+read twice) >> 126 MB L2",
+    }
+
+
+# ------------------------------------------------------------------------------------------------------------------
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from cppflow_b200 import ops, _lib
+    from cppflow_b200.robot import get_robot
+    from cppflow_b200.synthetic import synthetic_problem, synthetic_seeds_host
+    from cppflow_b200.lm_hyper_parameters import all_terms_parameters
+    from cppflow_b200.distributed import gather_costs_and_argmin
+    import ctypes
+
+    lib = _lib.load()
+    robot = get_robot("fetch")
+    P, T, D = args.paths, args.waypoints, robot.ndof
+    problem = synthetic_problem(robot, T, seed=0, device=dev)
+    _, x_host = synthetic_seeds_host(robot, P, T, seed=0, shard=rank, pin=True)
+    x0 = x_host.to(dev)
+    x_out = torch.empty_like(x0)
+    prm = ops.make_params(all_terms_parameters())
+    ob = problem.obstacle_tables
+    rid = robot.robot_id
+    evals_per_step = P * T
+
+    def step(src=x0, dst=x_out):
+        return ops.lm_full_step(rid, D, prm, src, None, problem.target_path, P, T, ob, True, out=dst)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    # warm up the once-per-job tail too (path metrics kernel, NCCL gather, torch argmin): first calls load modules
+    gather_costs_and_argmin(ops.path_metrics(rid, D, x_out, problem.target_path, P, T, ob), problem.constraints, rank, world)
+    barrier()
+
+    # ---- headline: K steps, inputs resident in HBM, CUDA events, max over ranks
+    sampler = ClockSampler(physical_gpu_index(local_rank), period=float(os.environ.get("BENCH_CLOCK_PERIOD", "0.01")))
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    dbg = [] if os.environ.get("BENCH_DEBUG_EVENTS") else None
+    for _ in range(args.steps):
+        step()
+        if dbg is not None:
+            dbg.append(torch.cuda.Event(enable_timing=True))
+            dbg[-1].record()
+    if dbg is not None:
+        torch.cuda.synchronize(dev)
+        ts = [e0.elapsed_time(dbg[0])] + [dbg[i].elapsed_time(dbg[i + 1]) for i in range(len(dbg) - 1)]
+        print("per-step ms:", [round(t, 2) for t in ts[:12]], "...", [round(t, 2) for t in ts[-6:]], file=sys.stderr)
+    metrics = ops.path_metrics(rid, D, x_out, problem.target_path, P, T, ob)
+    best_cost, best_rank, best_idx = gather_costs_and_argmin(metrics, problem.constraints, rank, world)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * evals_per_step / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers in, host buffers out, through the public API, copies inside the timed region
+    from cppflow_b200.pipeline import HostPipeline
+
+    pipe = HostPipeline(problem, P, all_terms_parameters())
+    out_host = torch.empty_like(x_host).pin_memory()
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        pipe.refine(x_host, out_host)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(e2e_steps):
+        pipe.refine(x_host, out_host)
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * evals_per_step / (e2e_ms / e2e_steps * 1e-3)
+    h2d = x_host.numel() * 4
+    d2h = out_host.numel() * 4
+
+    # ---- per-kernel durations (live, CUDA events on the launching stream) for the roofline
+    n_prof = max(5, min(args.steps, 50))
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_prof)]
+    ws = ops._workspace(dev, lib.cppflow_lm_full_workspace_bytes(rid, P, T), "lm_full")
+    cu, tc, no = ops._obs(ob)
+    st = _lib.stream_ptr(dev)
+    for i in range(n_prof):
+        ev[i][0].record()
+        _lib.check(lib.cppflow_lm_full_assemble(rid, prm, _lib.ptr(x0), None, _lib.ptr(problem.target_path), P, T, cu, tc,
+                                                no, _lib.ptr(ws), ws.numel(), st))
+        ev[i][1].record()
+        _lib.check(lib.cppflow_lm_full_solve(rid, prm, _lib.ptr(x0), P, T, 1, _lib.ptr(ws), ws.numel(), _lib.ptr(x_out), st))
+        ev[i][2].record()
+    torch.cuda.synchronize(dev)
+    ms_assemble = statistics.mean(ev[i][0].elapsed_time(ev[i][1]) for i in range(n_prof))
+    ms_solve = statistics.mean(ev[i][1].elapsed_time(ev[i][2]) for i in range(n_prof))
+
+    # ---- FP32 peak measured live (MEASURED_PEAKS.json has no FP32 entry)
+    scratch = torch.zeros(16, device=dev)
+    flops = ctypes.c_double(0.0)
+    blocks, iters = 148 * 2 * 4, 4096
+    for _ in range(2):
+        _lib.check(lib.cppflow_fp32_probe(blocks, iters, _lib.ptr(scratch), ctypes.byref(flops), st))
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for _ in range(5):
+        _lib.check(lib.cppflow_fp32_probe(blocks, iters, _lib.ptr(scratch), ctypes.byref(flops), st))
+    pe1.record()
+    torch.cuda.synchronize(dev)
+    fp32_peak_tflops = 5 * flops.value / (pe0.elapsed_time(pe1) * 1e-3) / 1e12
+
+    peaks = {}
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    traffic = None
+    try:
+        with open(os.path.join(REPO, "profiles", "traffic.json")) as f:
+            traffic = json.load(f)
+    except Exception:
+        pass
+
+    achieved_tflops = F_ASSEMBLE * evals_per_step / (ms_assemble * 1e-3) / 1e12
+    ws_bytes = lib.cppflow_lm_full_workspace_bytes(rid, P, T)
+    roofline = {
+        "kernel": "lm_assemble_kernel<Fetch> (FK + Jacobian + pose error + capsule distances + normal-equation blocks)",
+        "bound": "fp32",
+        "achieved": achieved_tflops,
+        "peak": fp32_peak_tflops,
+        "unit": "TFLOP/s",
+        "frac": achieved_tflops / fp32_peak_tflops,
+        "peak_source": "measured live: cppflow_fp32_probe (8 independent FMA chains/thread, 148x8 CTAs x 1024 thr)",
+        "flop_per_eval": F_ASSEMBLE,
+        "evals_per_launch": evals_per_step,
+        "ms_per_launch": ms_assemble,
+        "traffic": (traffic or {}).get("lm_assemble_kernel"),
+    }
+    solve_bytes = 3 * ws_bytes + 2 * x0.numel() * 4  # read blocks, write (S^-1,u), read them back; read q, write x
+    roofline_solve = {
+        "kernel": "lm_block_solve_kernel<Fetch> (block Cholesky sweep, one thread per path)",
+        "bound": "hbm",
+        "achieved": solve_bytes / (ms_solve * 1e-3) / 1e9,
+        "peak": hbm_peak,
+        "unit": "GB/s",
+        "frac": solve_bytes / (ms_solve * 1e-3) / 1e9 / hbm_peak,
+        "peak_source": hbm_src,
+        "bytes_per_launch": solve_bytes,
+        "ms_per_launch": ms_solve,
+        "traffic": (traffic or {}).get("lm_block_solve_kernel"),
+    }
+    step_tflops = F_STEP_SURVEY * evals_per_step / (ms_per_step * 1e-3) / 1e12
+    roofline_step = {
+        "what": "whole fused iteration, SURVEY 8d figure of 9.1 kFLOP per evaluation",
+        "bound": "fp32", "achieved": step_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
+        "frac": step_tflops / fp32_peak_tflops,
+        "hbm_algorithmic_gbs": BYTES_PER_EVAL * evals_per_step / (ms_per_step * 1e-3) / 1e9,
+        "hbm_peak_gbs": hbm_peak,
+    }
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, dt, cores = cpu_reference_step_rate(T, args.cpu_sample_paths, 2, 1)
+        cpu_baseline = {
+            "value": rate, "unit": "waypoint-evals/s", "cores": cores, "kind": "port",
+            "sample": f"{args.cpu_sample_paths} of {P} paths x {T} waypoints, 2 timed steps ({dt:.2f} s each) of the oracle "
+                      f"port of the reference's dense torch path (get_r_and_J all terms + _lm_full_step), fp32, "
+                      f"torch {torch.__version__}",
+        }
+
+    line = {
+        "metric": "waypoint FK+Jac+collision+LM evals/s",
+        "value": value,
+        "unit": "waypoint-evals/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config(args, world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "waypoint-evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": wall / e2e_steps * 1e3, "steps": e2e_steps,
+                "api": "cppflow_b200.pipeline.HostPipeline.refine(host x -> host x_new), pinned host buffers"},
+        "gpu_launches": args.steps * 2 + 1,
+        "roofline": roofline,
+        "roofline_solve": roofline_solve,
+        "roofline_step": roofline_step,
+        "kernel_ms": {"lm_assemble_kernel": ms_assemble, "lm_block_solve_kernel": ms_solve},
+        "cpu_baseline": cpu_baseline,
+        "argmin": {"cost": best_cost, "rank": best_rank, "path": best_idx},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -72,10 +72,14 @@ _PROTOTYPES = {
     "cppflow_lm_full_workspace_bytes": (_SZ, [_I, _I64, _I64]),
     "cppflow_lm_full_step": (_I, [_I, C.POINTER(LmParamsC), _VP, _VP, _VP, _I64, _I64, c_float_p, c_float_p, _I, _I,
                                   _VP, _SZ, _VP, _VP]),
+    "cppflow_lm_full_assemble": (_I, [_I, C.POINTER(LmParamsC), _VP, _VP, _VP, _I64, _I64, c_float_p, c_float_p, _I, _VP,
+                                      _SZ, _VP]),
+    "cppflow_lm_full_solve": (_I, [_I, C.POINTER(LmParamsC), _VP, _I64, _I64, _I, _VP, _SZ, _VP, _VP]),
     "cppflow_joint_limit_flags": (_I, [_I, _VP, _I64, _F, _F, _VP, _VP]),
     "cppflow_dp_search_workspace_bytes": (_SZ, [_I64, _I64]),
     "cppflow_dp_search": (_I, [_I, _VP, _VP, _VP, _I64, _I64, _VP, _SZ, _VP, _VP, _VP, _VP, _VP]),
     "cppflow_path_metrics": (_I, [_I, _VP, _VP, _I64, _I64, c_float_p, c_float_p, _I, _VP, _VP]),
+    "cppflow_fp32_probe": (_I, [_I, _I, _VP, C.POINTER(C.c_double), _VP]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
 

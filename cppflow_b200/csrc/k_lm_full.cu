@@ -289,10 +289,9 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
 }
 
 template <class M>
-static int launch_full(const cppflow_lm_params* p, const float* q, const float* xv, const float* target, int64_t P,
-                       int64_t T, const Obstacles& ob, int do_clamp, float* ws, float* x_out, cudaStream_t st) {
-    AssembleParams ap{};
-    SolveParams sp{};
+static void make_params(const cppflow_lm_params* p, int n_obstacles, int do_clamp, AssembleParams& ap, SolveParams& sp) {
+    ap = AssembleParams{};
+    sp = SolveParams{};
     ap.lambda = p->lm_lambda;
     ap.a_pos = p->alpha_position;
     ap.a_rot = p->alpha_rotation;
@@ -311,12 +310,33 @@ static int launch_full(const cppflow_lm_params* p, const float* q, const float* 
     ap.use_virtual = p->use_virtual_configs;
     ap.n_virtual = p->n_virtual_configs;
     ap.use_self = p->use_self_collisions;
-    ap.use_env = p->use_env_collisions && ob.n > 0;
+    ap.use_env = p->use_env_collisions && n_obstacles > 0;
     sp.do_clamp = do_clamp;
+}
+
+template <class M>
+static int launch_assemble(const cppflow_lm_params* p, const float* q, const float* xv, const float* target, int64_t P,
+                           int64_t T, const Obstacles& ob, float* ws, cudaStream_t st) {
+    AssembleParams ap;
+    SolveParams sp;
+    make_params<M>(p, ob.n, 0, ap, sp);
     const size_t sh = sizeof(float) * ABLOCK * SmemLayout<M>::N_FULL;
-    cudaError_t e = cudaFuncSetAttribute(lm_assemble_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
-    if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    static bool attr_set = false;  // per template instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(lm_assemble_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+        if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
     lm_assemble_kernel<M><<<grid_for(P * T, ABLOCK), ABLOCK, sh, st>>>(q, xv, target, P, T, ob, ap, ws);
+    return CPPFLOW_OK;
+}
+
+template <class M>
+static int launch_solve(const cppflow_lm_params* p, const float* q, int64_t P, int64_t T, int do_clamp, float* ws,
+                        float* x_out, cudaStream_t st) {
+    AssembleParams ap;
+    SolveParams sp;
+    make_params<M>(p, 0, do_clamp, ap, sp);
     lm_block_solve_kernel<M><<<grid_for(P, 32), 32, 0, st>>>(q, P, T, sp, ws, x_out);
     return CPPFLOW_OK;
 }
@@ -340,27 +360,58 @@ extern "C" size_t cppflow_lm_full_workspace_bytes(int robot, int64_t P, int64_t 
     }
 }
 
-extern "C" int cppflow_lm_full_step(int robot, const cppflow_lm_params* params, const float* d_q, const float* d_xv,
-                                    const float* d_target, int64_t P, int64_t T, const float* h_cuboids,
-                                    const float* h_Tcuboids, int n_obstacles, int do_clamp, void* d_workspace,
-                                    size_t workspace_bytes, float* d_x_out, void* stream) {
+static int check_common(int robot, const cppflow_lm_params* params, int64_t P, int64_t T, const void* d_workspace,
+                        size_t workspace_bytes) {
     CPPFLOW_CHECK_ARG(params != nullptr, "params");
     CPPFLOW_CHECK_ARG(P >= 0 && T >= 0, "P, T");
-    if (P == 0 || T == 0) return CPPFLOW_OK;
-    CPPFLOW_CHECK_ARG(d_q && d_x_out && d_workspace, "null pointer");
-    CPPFLOW_CHECK_ARG(!params->use_pose || d_target, "target path required when use_pose");
+    CPPFLOW_CHECK_ARG(d_workspace != nullptr, "workspace");
     CPPFLOW_CHECK_ARG(!params->use_virtual_configs || (params->n_virtual_configs > 0 && 2 * params->n_virtual_configs < T),
                       "2 * n_virtual_configs must be < T (optimization_utils.py:457-459)");
     CPPFLOW_CHECK_ARG(((uintptr_t)d_workspace & 15) == 0, "workspace must be 16-byte aligned");
     if (workspace_bytes < cppflow_lm_full_workspace_bytes(robot, P, T))
-        return fail(CPPFLOW_E_WORKSPACE, "cppflow_lm_full_step: workspace too small (%zu < %zu)", workspace_bytes,
+        return fail(CPPFLOW_E_WORKSPACE, "lm_full: workspace too small (%zu < %zu)", workspace_bytes,
                     cppflow_lm_full_workspace_bytes(robot, P, T));
+    return CPPFLOW_OK;
+}
+
+extern "C" int cppflow_lm_full_assemble(int robot, const cppflow_lm_params* params, const float* d_q, const float* d_xv,
+                                        const float* d_target, int64_t P, int64_t T, const float* h_cuboids,
+                                        const float* h_Tcuboids, int n_obstacles, void* d_workspace,
+                                        size_t workspace_bytes, void* stream) {
+    if (P == 0 || T == 0) return CPPFLOW_OK;
+    if (int rc = check_common(robot, params, P, T, d_workspace, workspace_bytes)) return rc;
+    CPPFLOW_CHECK_ARG(d_q != nullptr, "null pointer");
+    CPPFLOW_CHECK_ARG(!params->use_pose || d_target, "target path required when use_pose");
     Obstacles ob;
     if (int rc = make_obstacles(h_cuboids, h_Tcuboids, n_obstacles, ob)) return rc;
     int rc = CPPFLOW_OK;
-    CPPFLOW_DISPATCH_ROBOT(robot, rc = launch_full<M>(params, d_q, d_xv, d_target, P, T, ob, do_clamp,
-                                                      (float*)d_workspace, d_x_out, (cudaStream_t)stream));
+    CPPFLOW_DISPATCH_ROBOT(robot, rc = launch_assemble<M>(params, d_q, d_xv, d_target, P, T, ob, (float*)d_workspace,
+                                                          (cudaStream_t)stream));
     if (rc) return rc;
     CPPFLOW_CHECK_LAUNCH();
     return CPPFLOW_OK;
+}
+
+extern "C" int cppflow_lm_full_solve(int robot, const cppflow_lm_params* params, const float* d_q, int64_t P, int64_t T,
+                                     int do_clamp, void* d_workspace, size_t workspace_bytes, float* d_x_out,
+                                     void* stream) {
+    if (P == 0 || T == 0) return CPPFLOW_OK;
+    if (int rc = check_common(robot, params, P, T, d_workspace, workspace_bytes)) return rc;
+    CPPFLOW_CHECK_ARG(d_q && d_x_out, "null pointer");
+    int rc = CPPFLOW_OK;
+    CPPFLOW_DISPATCH_ROBOT(robot, rc = launch_solve<M>(params, d_q, P, T, do_clamp, (float*)d_workspace, d_x_out,
+                                                       (cudaStream_t)stream));
+    if (rc) return rc;
+    CPPFLOW_CHECK_LAUNCH();
+    return CPPFLOW_OK;
+}
+
+extern "C" int cppflow_lm_full_step(int robot, const cppflow_lm_params* params, const float* d_q, const float* d_xv,
+                                    const float* d_target, int64_t P, int64_t T, const float* h_cuboids,
+                                    const float* h_Tcuboids, int n_obstacles, int do_clamp, void* d_workspace,
+                                    size_t workspace_bytes, float* d_x_out, void* stream) {
+    if (int rc = cppflow_lm_full_assemble(robot, params, d_q, d_xv, d_target, P, T, h_cuboids, h_Tcuboids, n_obstacles,
+                                          d_workspace, workspace_bytes, stream))
+        return rc;
+    return cppflow_lm_full_solve(robot, params, d_q, P, T, do_clamp, d_workspace, workspace_bytes, d_x_out, stream);
 }

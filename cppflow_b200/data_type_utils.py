@@ -1,0 +1,129 @@
+"""Problem loading with the reference's entry point (cppflow/data_type_utils.py: problem_from_filename :148-219,
+get_obstacles :87-145, offset_target_path :55-84, problem lists :24-52).
+
+The problem yamls and path csvs of the reference are packed into cppflow_b200/data/{problems.json,
+target_paths.npz} by data/make_problem_data.py (the GPU box has no copy of the reference tree).  klampt is not
+needed: the only link pose the offsets use is `torso_lift_link` at q = 0, which is the fixed origin of the torso
+joint (identity orientation, data_type_utils.py:73)."""
+import json
+import os
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import config
+from .data_types import Constraints, Problem, DEFAULT_CONSTRAINTS
+from .robot import Robot, get_robot
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+ALL_PROBLEM_FILENAMES = [
+    "fetch_arm__hello", "fetch_arm__circle", "fetch_arm__rot_yz2", "fetch_arm__s", "fetch_arm__square",
+    "fetch__circle", "fetch__hello", "fetch__rot_yz2", "fetch__s", "fetch__square",
+    "panda__1cube", "panda__2cubes", "panda__flappy_bird",
+]
+ALL_OBS_PROBLEM_FILENAMES = [
+    "fetch_arm__circle", "fetch_arm__s", "fetch_arm__square", "fetch__circle", "fetch__s", "fetch__square",
+    "panda__1cube", "panda__2cubes", "panda__flappy_bird",
+]
+
+# world position of the frames `path_offset_frame` may name, at q = 0
+_FRAME_ORIGIN_AT_ZERO = {"world": (0.0, 0.0, 0.0), "torso_lift_link": (-0.086875, 0.0, 0.37743)}
+
+_problems_cache = None
+_paths_cache = None
+
+
+def _problems() -> Dict:
+    global _problems_cache
+    if _problems_cache is None:
+        with open(os.path.join(_DATA, "problems.json")) as f:
+            _problems_cache = json.load(f)
+    return _problems_cache
+
+
+def _paths():
+    global _paths_cache
+    if _paths_cache is None:
+        _paths_cache = np.load(os.path.join(_DATA, "target_paths.npz"))
+    return _paths_cache
+
+
+def _quat_to_R(q):
+    w, x, y, z = q
+    return np.array([
+        [1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+        [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+        [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)],
+    ])
+
+
+def _R_to_quat(R):
+    t = np.array([1 + R[0, 0] + R[1, 1] + R[2, 2], 1 + R[0, 0] - R[1, 1] - R[2, 2],
+                  1 - R[0, 0] + R[1, 1] - R[2, 2], 1 - R[0, 0] - R[1, 1] + R[2, 2]])
+    i = int(np.argmax(t))
+    if i == 0:
+        q = np.array([t[0], R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    elif i == 1:
+        q = np.array([R[2, 1] - R[1, 2], t[1], R[1, 0] + R[0, 1], R[0, 2] + R[2, 0]])
+    elif i == 2:
+        q = np.array([R[0, 2] - R[2, 0], R[1, 0] + R[0, 1], t[2], R[1, 2] + R[2, 1]])
+    else:
+        q = np.array([R[1, 0] - R[0, 1], R[2, 0] + R[0, 2], R[2, 1] + R[1, 2], t[3]])
+    q = q / (2 * np.sqrt(t[i]))
+    return q if q[0] >= 0 else -q
+
+
+def offset_target_path(target_path: np.ndarray, path_offset_frame: str, xyz_offset: List[float],
+                       R_offset: List[List[float]]) -> torch.Tensor:
+    """data_type_utils.py:55-84: translate by xyz_offset + frame origin; right-multiply each pose's rotation."""
+    path = target_path.copy()
+    frame_origin = _FRAME_ORIGIN_AT_ZERO[path_offset_frame]
+    for i in range(3):
+        path[:, i] += xyz_offset[i] + frame_origin[i]
+    R_off = np.array(R_offset, dtype=np.float64)
+    if not np.allclose(R_off, np.eye(3)):
+        for i in range(path.shape[0]):
+            path[i, 3:7] = _R_to_quat(_quat_to_R(path[i, 3:7]) @ R_off)
+    return torch.tensor(path, dtype=torch.float32)
+
+
+def get_obstacles(problem_dict: Dict, device=None):
+    """data_type_utils.py:87-145: cuboid = [-sx/2,-sy/2,-sz/2, sx/2,sy/2,sz/2]; Tcuboid 4x4 with Tcuboid[3,3] left 0."""
+    device = config.DEVICE if device is None else device
+    obstacles, Tcuboids, cuboids = [], [], []
+    for obs in problem_dict.get("obstacles", []):
+        obs = dict(obs)
+        obs["x"] += problem_dict["obstacle_xyz_offset"][0]
+        obs["y"] += problem_dict["obstacle_xyz_offset"][1]
+        obs["z"] += problem_dict["obstacle_xyz_offset"][2]
+        assert abs(obs["roll"]) < 1e-8 and abs(obs["pitch"]) < 1e-8 and abs(obs["yaw"]) < 1e-8
+        cuboids.append(torch.tensor([-obs["size_x"] / 2, -obs["size_y"] / 2, -obs["size_z"] / 2,
+                                     obs["size_x"] / 2, obs["size_y"] / 2, obs["size_z"] / 2], device=device))
+        Tc = torch.zeros((4, 4))
+        Tc[:3, :3] = torch.eye(3)
+        Tc[0, 3], Tc[1, 3], Tc[2, 3] = obs["x"], obs["y"], obs["z"]
+        Tcuboids.append(Tc.to(device))
+        obstacles.append(obs)
+    return obstacles, Tcuboids, cuboids
+
+
+def problem_from_filename(constraints: Optional[Constraints], problem_filename: str, filepath_override: Optional[str] = None,
+                          robot: Optional[Robot] = None, device=None) -> Problem:
+    """Build a Problem (target path on `device`) from one of the packed problem definitions."""
+    assert "yaml" not in problem_filename, "problem_filename should not include the .yaml file extension"
+    assert filepath_override is None, "only the packed problem definitions are available (data/problems.json)"
+    device = config.DEVICE if device is None else device
+    d = _problems()[problem_filename]
+    if robot is None:
+        robot = get_robot(d["robot"])
+    obstacles, Tcuboids, cuboids = get_obstacles(d, device=device)
+    target_path = offset_target_path(_paths()[d["path_name"]], d["path_offset_frame"], d["path_xyz_offset"],
+                                     d["path_R_offset"]).to(device)
+    return Problem(constraints if constraints is not None else DEFAULT_CONSTRAINTS, target_path, None, robot,
+                   d["path_name"], problem_filename, obstacles, Tcuboids, cuboids, [])
+
+
+def get_all_problems(device=None) -> List[Problem]:
+    return [problem_from_filename(None, name, device=device) for name in ALL_PROBLEM_FILENAMES]

@@ -1,0 +1,180 @@
+"""Planner front-end with the reference's control flow (cppflow/planners.py: Planner._run_pipeline :191-292,
+PlannerSearcher :301-336, CppFlowPlanner.generate_plan :345-468).
+
+IKFlow (the conditional normalising flow that proposes the k candidate joint paths, planners.py:116-172) is out of
+scope - its pretrained weights are not available offline - so the candidate generator is a pluggable callable
+`(problem, k) -> [k, T, ndof]`.  The default, `LmIkCandidateGenerator`, draws k smooth random joint paths and pulls
+each waypoint onto the target pose with a few pose-only LM steps of the CUDA kernel."""
+from time import time
+from typing import Callable, Dict, Optional, Tuple
+
+import torch
+
+from .collision_detection import qpaths_batched_collisions
+from .config import DEVICE, OPTIMIZATION_CONVERGENCE_THRESHOLD, SUCCESS_THRESHOLD_initial_q_norm_dist
+from .data_types import PathReport, PlannerResult, PlannerSettings, Problem, TimingData
+from .evaluation_utils import get_mjacs
+from .optimization import run_lm_optimization
+from .optimization_utils import path_metrics
+from .search import dp_search
+from . import ops
+from .lm_hyper_parameters import ALT_LOSS_V2_1_POSE
+
+DEFAULT_RERUN_NEW_K = 125  # planners.py:47
+
+CandidateGenerator = Callable[[Problem, int], torch.Tensor]
+
+
+class LmIkCandidateGenerator:
+    """k candidate paths = k random joint-space offsets of a random smooth path, each waypoint refined onto the target
+    pose by `n_steps` pose-only LM steps (csrc/k_pose.cu).  A stand-in for IKFlow sampling, not a reimplementation."""
+
+    def __init__(self, n_steps: int = 6, seed: int = 0):
+        self.n_steps = n_steps
+        self.gen = torch.Generator().manual_seed(seed)
+
+    def __call__(self, problem: Problem, k: int) -> torch.Tensor:
+        robot, T = problem.robot, problem.n_timesteps
+        dev = problem.target_path.device
+        lim = torch.tensor(robot.actuated_joints_limits, dtype=torch.float32)
+        mid, half = lim.mean(dim=1), (lim[:, 1] - lim[:, 0]) / 2
+        base = mid + 0.6 * half * (2 * torch.rand((k, 1, robot.ndof), generator=self.gen) - 1)
+        x = base.expand(k, T, robot.ndof).reshape(k * T, robot.ndof).contiguous().to(dev)
+        prm = ops.make_params(ALT_LOSS_V2_1_POSE)
+        for _ in range(self.n_steps):
+            x = ops.lm_pose_step(robot.robot_id, robot.ndof, prm, x, problem.target_path, True)
+        return x.reshape(k, T, robot.ndof)
+
+
+def report_from_qpath(qpath: torch.Tensor, problem: Problem) -> PathReport:
+    """Capsule-based stand-in for plan_from_qpath (data_type_utils.py:244-276; its klampt mesh checks are out of scope)."""
+    m = path_metrics(problem, qpath.contiguous(), 1).cpu()[0].tolist()
+    c = problem.constraints
+    valid = (m[0] < c.max_allowed_position_error_cm and m[1] < c.max_allowed_rotation_error_deg
+             and m[2] < c.max_allowed_mjac_deg and m[3] < c.max_allowed_mjac_cm and m[5] >= 0 and m[6] >= 0)
+    return PathReport(qpath, m[0], m[1], m[2], m[3], m[4], m[5], m[6], bool(valid))
+
+
+class Planner:
+    def __init__(self, settings: PlannerSettings, robot, candidate_generator: Optional[CandidateGenerator] = None):
+        self._cfg = settings
+        self._robot = robot
+        self._candidates = candidate_generator if candidate_generator is not None else LmIkCandidateGenerator()
+
+    def set_settings(self, settings: PlannerSettings):
+        self._cfg = settings
+
+    @property
+    def robot(self):
+        return self._robot
+
+    @property
+    def name(self) -> str:
+        return str(self.__class__.__name__)
+
+    def _run_pipeline(self, problem: Problem, **kwargs) -> Tuple[torch.Tensor, bool, TimingData, Dict, Tuple]:
+        """Candidates -> collision flags -> dp_search (planners.py:191-292)."""
+        existing_q_data = kwargs.get("rerun_data")
+        t0 = time()
+        k = self._cfg.k if existing_q_data is None else DEFAULT_RERUN_NEW_K
+        qs = self._candidates(problem, k)  # [k, T, ndof]
+        time_ikflow = time() - t0
+        if self._cfg.return_only_1st_plan:
+            return qs[0], False, TimingData(-1, time_ikflow, 0.0, 0.0, 0.0, 0.0), {}, (qs[0], None, None)
+
+        t0 = time()
+        k_current = qs.shape[0]
+        self_v, env_v = qpaths_batched_collisions(problem, qs)  # one launch for both flag sets
+        pct = torch.stack([self_v.sum(), env_v.sum()]).float().cpu() / (k_current * problem.n_timesteps) * 100  # one sync
+        assert pct[0] < 95.0, f"too many self collisions: {pct[0]} %"
+        assert pct[1] < 95.0, f"too many env collisions: {pct[1]} %"
+        if existing_q_data is not None:
+            qs_prev, self_prev, env_prev = existing_q_data
+            qs = torch.cat([qs_prev, qs], dim=0)
+            self_v = torch.cat([self_prev, self_v], dim=0)
+            env_v = torch.cat([env_prev, env_v], dim=0)
+        if problem.initial_configuration is not None:
+            qs[:, 0, :] = problem.initial_configuration.to(qs.device)
+            self_v[:, 0] = False
+            env_v[:, 0] = False
+        time_coll = time() - t0
+
+        t0 = time()
+        qpath_search = dp_search(self.robot, qs, self_v, env_v, verbosity=0)
+        q_data = (qs, self_v, env_v)
+        time_dp = time() - t0
+        return qpath_search, False, TimingData(-1, time_ikflow, time_coll, 0.0, time_dp, 0.0), {}, q_data
+
+    def generate_plan(self, problem: Problem, **kwargs) -> PlannerResult:
+        raise NotImplementedError()
+
+
+class PlannerSearcher(Planner):
+    """dp_search only (planners.py:301-336)."""
+
+    def generate_plan(self, problem: Problem, **kwargs) -> PlannerResult:
+        assert problem.robot.name == self.robot.name
+        t0 = time()
+        qpath_search, _, td, debug_info, _ = self._run_pipeline(problem, **kwargs)
+        return PlannerResult(report_from_qpath(qpath_search, problem),
+                             TimingData(time() - t0, td.ikflow, td.coll_checking, td.batch_opt, td.dp_search, 0.0), [], [],
+                             debug_info)
+
+
+class CppFlowPlanner(Planner):
+    """dp_search followed by LM optimisation (planners.py:339-468)."""
+
+    def generate_plan(self, problem: Problem, **kwargs) -> PlannerResult:
+        t0 = kwargs.get("t0", time())
+        rerun_data = kwargs.get("rerun_data")
+        search_qpath, is_valid, td, debug_info, q_data = self._run_pipeline(problem, **kwargs)
+
+        def time_is_exceeded():
+            return time() - t0 > self._cfg.tmax_sec
+
+        def return_(qpath):
+            return PlannerResult(report_from_qpath(qpath, problem),
+                                 TimingData(time() - t0, td.ikflow, td.coll_checking, td.batch_opt, td.dp_search, td.optimizer),
+                                 [], [], debug_info)
+
+        if self._cfg.return_only_1st_plan:
+            return return_(search_qpath)
+        if self._cfg.do_rerun_if_large_dp_search_mjac:
+            mjac_deg, mjac_cm = get_mjacs(problem.robot, search_qpath)
+            if mjac_deg > self._cfg.rerun_mjac_threshold_deg or mjac_cm > self._cfg.rerun_mjac_threshold_cm:
+                kwargs["rerun_data"] = q_data
+                search_qpath, is_valid, td, debug_info, q_data = self._run_pipeline(problem, **kwargs)
+        if time_is_exceeded():
+            return return_(search_qpath)
+        if (not self._cfg.anytime_mode_enabled) and is_valid:
+            return return_(search_qpath)
+
+        t0_opt = time()
+        if self._cfg.anytime_mode_enabled:
+            result = run_lm_optimization(problem, search_qpath, max_n_steps=75, tmax_sec=self._cfg.tmax_sec - (time() - t0),
+                                         return_if_valid_after_n_steps=int(1e8),
+                                         convergence_threshold=OPTIMIZATION_CONVERGENCE_THRESHOLD,
+                                         verbosity=self._cfg.verbosity)
+        else:
+            result = run_lm_optimization(problem, search_qpath, max_n_steps=20, tmax_sec=self._cfg.tmax_sec - (time() - t0),
+                                         return_if_valid_after_n_steps=0, convergence_threshold=1e6,
+                                         verbosity=self._cfg.verbosity)
+        td.optimizer = time() - t0_opt
+        debug_info["n_optimization_steps"] = result.n_steps_taken
+        x_opt = result.x_opt.detach()
+
+        if result.is_valid:
+            if problem.initial_configuration is None:
+                return return_(x_opt)
+            init = problem.initial_configuration.to(x_opt.device)
+            if torch.norm(init - x_opt[0]) < SUCCESS_THRESHOLD_initial_q_norm_dist:
+                return return_(x_opt)
+            x_opt_swapped = torch.cat((init, x_opt[1:]), dim=0)
+            if report_from_qpath(x_opt_swapped, problem).is_valid:
+                return return_(x_opt_swapped)
+            return return_(x_opt)
+        if self._cfg.do_rerun_if_optimization_fails and (rerun_data is None) and (not time_is_exceeded()):
+            kwargs["rerun_data"] = q_data
+            kwargs["t0"] = t0
+            return self.generate_plan(problem, **kwargs)
+        return return_(x_opt)

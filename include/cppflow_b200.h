@@ -130,6 +130,16 @@ int cppflow_lm_full_step(int robot, const cppflow_lm_params* params, const float
                          int n_obstacles, int do_clamp, void* d_workspace, size_t workspace_bytes, float* d_x_out,
                          void* stream);
 
+/* The two halves of cppflow_lm_full_step, exposed so a host pipeline can overlap the assembly of one chunk of paths
+ * with the solve of another on different streams: assemble writes the packed (A_tt, b_t) blocks to the workspace,
+ * solve consumes them and writes clamp(x + dx). */
+int cppflow_lm_full_assemble(int robot, const cppflow_lm_params* params, const float* d_q, const float* d_xv,
+                             const float* d_target, int64_t P, int64_t T, const float* h_cuboids,
+                             const float* h_Tcuboids, int n_obstacles, void* d_workspace, size_t workspace_bytes,
+                             void* stream);
+int cppflow_lm_full_solve(int robot, const cppflow_lm_params* params, const float* d_q, int64_t P, int64_t T,
+                          int do_clamp, void* d_workspace, size_t workspace_bytes, float* d_x_out, void* stream);
+
 /* joint_limit_almost_violations_3d(robot, qs, eps_revolute, eps_prismatic) -> float32 0/1 [n]  (search.py:25-52) */
 int cppflow_joint_limit_flags(int robot, const float* d_q, int64_t n, float eps_revolute, float eps_prismatic,
                               float* d_flags, void* stream);
@@ -149,6 +159,10 @@ int cppflow_dp_search(int robot, const float* d_q, const uint8_t* d_self_flags, 
  *  trajectory length rad, min capsule self distance m, min capsule env distance m (+inf if no obstacles), 0}. */
 int cppflow_path_metrics(int robot, const float* d_q, const float* d_target, int64_t P, int64_t T,
                          const float* h_cuboids, const float* h_Tcuboids, int n_obstacles, float* d_out, void* stream);
+
+/* Measurement aid (no reference counterpart): dependent-free FP32 FMA loop on `blocks` x 1024 threads, used by
+ * bench.py to measure the FP32 roofline denominator on the box.  *flops_out = FLOPs of the launch. */
+int cppflow_fp32_probe(int blocks, int iters, float* d_scratch, double* flops_out, void* stream);
 
 #ifdef __cplusplus
 }

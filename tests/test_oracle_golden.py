@@ -181,7 +181,8 @@ def test_differencing_residual_is_row_major_delta():
 @pytest.mark.parametrize("r", ROBOTS)
 def test_batched_pose_lm_equals_dense_lm(golden, r):
     """tests/optimization_test.py:74-100: batched pose step == dense full step on pose-only params
-    (J, r atol 1e-5; x atol 5e-3)."""
+    (J, r atol 1e-5; x atol 5e-3).  J and r are compared in the reference's fp32; x in fp64, because in fp32 the
+    two solvers only agree up to the null-space noise measured in test_reference_fp32_null_space_noise."""
     m = R.get_model(r)
     x, tgt = T(golden[f"{r}/lm/x"]), T(golden[f"{r}/lm/target"])
     xb, Jb, eb = L.levenberg_marquardt_only_pose(m, x, tgt, L.ALT_LOSS_V2_1_POSE, return_residual=True)
@@ -190,8 +191,26 @@ def test_batched_pose_lm_equals_dense_lm(golden, r):
     for i in range(n):
         torch.testing.assert_close(Jd["pose"][6 * i : 6 * i + 6, D * i : D * i + D], Jb[i], atol=1e-5, rtol=0)
     torch.testing.assert_close(rd["pose"].reshape(n, 6, 1), eb, atol=1e-5, rtol=0)
-    xd = L.lm_full_step(L.stack_rows(Jd), L.stack_rows(rd), x, 1e-6)
-    torch.testing.assert_close(xd, xb, atol=5e-3, rtol=0)
+    x64, t64 = x.double(), tgt.double()
+    xb = L.levenberg_marquardt_only_pose(m, x64, t64, L.ALT_LOSS_V2_1_POSE)
+    Jd, rd = L.get_r_and_J(L.ALT_LOSS_V2_1_POSE, m, x64, t64)
+    xd = L.lm_full_step(L.stack_rows(Jd), L.stack_rows(rd), x64, 1e-6)
+    torch.testing.assert_close(xd, xb, atol=1e-6, rtol=0)
+
+
+def test_reference_fp32_null_space_noise(golden):
+    """DESIGN.md 'numerics': with lambda = 1e-6 the fp32 normal equations of a 7/8-dof arm carry rounding noise in
+    the null space of J that 1/lambda amplifies; the reference's own fp32 step is > 1e-3 rad away from exact
+    arithmetic, which is why LM parity is defined against the fp64 oracle."""
+    m = R.get_model("fetch")
+    x, tgt = T(golden["fetch/lm/x"]), T(golden["fetch/lm/target"])
+    x32 = L.levenberg_marquardt_only_pose(m, x, tgt, L.ALT_LOSS_V2_1_POSE)
+    x64 = L.levenberg_marquardt_only_pose(m, x.double(), tgt.double(), L.ALT_LOSS_V2_1_POSE)
+    assert (x32.double() - x64).abs().max() > 1e-3
+    # ... while both reduce the pose error equally well (the noise lives in the null space)
+    e32, _ = L.get_6d_pose_errors(m, x32.double(), tgt.double())
+    e64, _ = L.get_6d_pose_errors(m, x64, tgt.double())
+    assert abs(e32.abs().max() - e64.abs().max()) < 1e-3
 
 
 def test_batched_equals_per_path_collision_flags(golden):
@@ -210,5 +229,5 @@ def test_batched_equals_per_path_collision_flags(golden):
 
 
 def test_geodesic_floor():
-    q = T([[1.0, 0, 0, 0]])
-    assert abs(geodesic_distance_between_quaternions(q, q).item() - 2 * math.acos(1 - 1e-7)) < 1e-6
+    q = T([[1.0, 0, 0, 0]], torch.float64)
+    assert abs(geodesic_distance_between_quaternions(q, q).item() - 2 * math.acos(1 - 1e-7)) < 1e-9
