@@ -8,6 +8,23 @@
 
 namespace cppflow {
 
+// constexpr square root (Newton) for the compile-time capsule half-lengths
+__host__ __device__ constexpr double csqrt(double x) {
+    if (x <= 0.0) return 0.0;
+    double r = x > 1.0 ? x : 1.0;
+    for (int i = 0; i < 60; ++i) r = 0.5 * (r + x / r);
+    return r;
+}
+template <class M>
+__host__ __device__ constexpr float cap_half_length(int c) {
+    const double dx = (double)M::cap(c, 3) - (double)M::cap(c, 0);
+    const double dy = (double)M::cap(c, 4) - (double)M::cap(c, 1);
+    const double dz = (double)M::cap(c, 5) - (double)M::cap(c, 2);
+    return (float)(0.5 * csqrt(dx * dx + dy * dy + dz * dz));
+}
+// slack added to every culling bound so that fp32 rounding can never cull a pair whose distance is < threshold
+#define CPPFLOW_CULL_MARGIN 1e-4f
+
 template <class M>
 struct PairTable {
     int a[M::NPAIR];
@@ -15,6 +32,7 @@ struct PairTable {
     int fa[M::NPAIR];  // link frame of capsule a / b
     int fb[M::NPAIR];
     float rsum[M::NPAIR];
+    float reach[M::NPAIR];  // half-lengths + radii + margin: |mid_a - mid_b| - reach is a lower bound of the distance
 };
 template <class M>
 __host__ __device__ constexpr PairTable<M> make_pair_table() {
@@ -25,6 +43,7 @@ __host__ __device__ constexpr PairTable<M> make_pair_table() {
         t.fa[p] = M::cap_frame(t.a[p]);
         t.fb[p] = M::cap_frame(t.b[p]);
         t.rsum[p] = M::cap(t.a[p], 6) + M::cap(t.b[p], 6);
+        t.reach[p] = t.rsum[p] + cap_half_length<M>(t.a[p]) + cap_half_length<M>(t.b[p]) + CPPFLOW_CULL_MARGIN;
     }
     return t;
 }
@@ -32,6 +51,7 @@ template <class M>
 struct CapTable {
     int frame[M::NCAP];
     float radius[M::NCAP];
+    float reach[M::NCAP];  // half-length + radius + margin
 };
 template <class M>
 __host__ __device__ constexpr CapTable<M> make_cap_table() {
@@ -39,6 +59,7 @@ __host__ __device__ constexpr CapTable<M> make_cap_table() {
     for (int c = 0; c < M::NCAP; ++c) {
         t.frame[c] = M::cap_frame(c);
         t.radius[c] = M::cap(c, 6);
+        t.reach[c] = M::cap(c, 6) + cap_half_length<M>(c) + CPPFLOW_CULL_MARGIN;
     }
     return t;
 }
@@ -96,12 +117,22 @@ __device__ __forceinline__ void load_capsule(const float* sm, int c, float (&P)[
     }
 }
 
-// signed distance of self-collision pair p; C1/C2 closest points on the two capsule axes, dist their distance
+// Signed distance of self-collision pair p; C2 = closest point on the axis of capsule b, nrm = unit vector from it
+// to the closest point on capsule a.  Pairs whose bounding spheres prove distance > cull_thr are skipped and
+// +INFINITY is returned (pass cull_thr = INFINITY to always get the exact distance).
 template <class M, int BLOCK>
-__device__ __forceinline__ float self_pair_distance(const float* sm, int p, float (&C2)[3], float (&nrm)[3]) {
+__device__ __forceinline__ float self_pair_distance(const float* sm, int p, float (&C2)[3], float (&nrm)[3],
+                                                    float cull_thr = INFINITY) {
     float P1[3], Q1[3], P2[3], Q2[3];
     load_capsule<BLOCK>(sm, c_pair_table<M>.a[p], P1, Q1);
     load_capsule<BLOCK>(sm, c_pair_table<M>.b[p], P2, Q2);
+    {
+        const float mx = (P1[0] + Q1[0]) - (P2[0] + Q2[0]);
+        const float my = (P1[1] + Q1[1]) - (P2[1] + Q2[1]);
+        const float mz = (P1[2] + Q1[2]) - (P2[2] + Q2[2]);
+        const float lim = cull_thr + c_pair_table<M>.reach[p];  // > 0 whenever a cull is intended
+        if (0.25f * (mx * mx + my * my + mz * mz) > lim * lim && lim > 0.f) return INFINITY;
+    }
     float s, t;
     segseg_closest(P1, Q1, P2, Q2, s, t);
     float diff[3];
@@ -151,11 +182,23 @@ __device__ __forceinline__ void self_pair_gradient(const float* sm, int p, const
 // signed distance of capsule c to obstacle o; Cw = closest point on the capsule axis (world), nrm = world normal
 template <class M, int BLOCK>
 __device__ __forceinline__ float env_capsule_distance(const float* sm, int c, const Obstacles& ob, int o,
-                                                      float (&Cw)[3], float (&nrm)[3]) {
+                                                      float (&Cw)[3], float (&nrm)[3], float cull_thr = INFINITY) {
     float P[3], Q[3], A[3], B[3];
     load_capsule<BLOCK>(sm, c, P, Q);
     to_box_frame(ob, o, P, A);
     to_box_frame(ob, o, Q, B);
+    {
+        // distance(segment midpoint, box) - half length - radius is a lower bound of the capsule-box distance
+        float dd = 0.f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float m = 0.5f * (A[r] + B[r]);
+            const float e = m - fminf(fmaxf(m, ob.lo[o][r]), ob.hi[o][r]);
+            dd = fmaf(e, e, dd);
+        }
+        const float lim = cull_thr + c_cap_table<M>.reach[c];
+        if (dd > lim * lim && lim > 0.f) return INFINITY;
+    }
     const float t = segbox_closest(A, B, ob.lo[o], ob.hi[o]);
     float diff[3];
 #pragma unroll

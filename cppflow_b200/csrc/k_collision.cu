@@ -87,7 +87,7 @@ collision_flags_kernel(const float* __restrict__ q, int64_t n, const Obstacles o
         float dmin = INFINITY;
         for (int p = 0; p < M::NPAIR; ++p) {
             float C2[3], nrm[3];
-            dmin = fminf(dmin, self_pair_distance<M, CBLOCK>(sm, p, C2, nrm));
+            dmin = fminf(dmin, self_pair_distance<M, CBLOCK>(sm, p, C2, nrm, 0.f));
         }
         self_flags[i] = dmin < 0.f ? 1 : 0;
     }
@@ -96,7 +96,7 @@ collision_flags_kernel(const float* __restrict__ q, int64_t n, const Obstacles o
         for (int o = 0; o < ob.n; ++o)
             for (int c = 0; c < M::NCAP; ++c) {
                 float Cw[3], nrm[3];
-                dmin = fminf(dmin, env_capsule_distance<M, CBLOCK>(sm, c, ob, o, Cw, nrm));
+                dmin = fminf(dmin, env_capsule_distance<M, CBLOCK>(sm, c, ob, o, Cw, nrm, 0.f));
             }
         env_flags[i] = dmin < 0.f ? 1 : 0;
     }

@@ -126,7 +126,7 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
     if (prm.use_self) {
         for (int p = 0; p < M::NPAIR; ++p) {
             float C2[3], nrm[3];
-            const float d = self_pair_distance<M, ABLOCK>(sm, p, C2, nrm);
+            const float d = self_pair_distance<M, ABLOCK>(sm, p, C2, nrm, 0.f);
             if (d < 0.f) {  // residual -alpha d > 0 (optimization_utils.py:653-660)
                 float g[D];
                 self_pair_gradient<M, ABLOCK>(sm, p, C2, nrm, g);
@@ -138,7 +138,7 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
         for (int o = 0; o < ob.n; ++o)
             for (int c = 0; c < M::NCAP; ++c) {
                 float Cw[3], nrm[3];
-                const float d = env_capsule_distance<M, ABLOCK>(sm, c, ob, o, Cw, nrm);
+                const float d = env_capsule_distance<M, ABLOCK>(sm, c, ob, o, Cw, nrm, 0.f);
                 if (d < 0.f) {
                     float g[D];
                     env_capsule_gradient<M, ABLOCK>(sm, c, Cw, nrm, g);
@@ -201,6 +201,15 @@ __device__ __forceinline__ void store_block(float* __restrict__ p, const float (
     for (int k = 0; k < NW / 4; ++k) s[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+template <int NW>
+__device__ __forceinline__ void prefetch_block(const float* p) {
+    prefetch_l1(p);
+    prefetch_l1(p + 32);
+    if (NW > 32) prefetch_l1(p + NW - 1);
+}
+constexpr int SOLVE_PF = 6;  // blocks prefetched ahead of the sweep (per thread, into L1)
+
 // Block-Thomas sweep, one thread per path.  Forward: S_t = A_t - E S_{t-1}^-1 E, y_t = b_t - E u_{t-1} with
 // E = -diag(beta), u_t = S_t^-1 y_t; the workspace block is overwritten by (S_t^-1, u_t).
 // Backward: dx_t = u_t + S_t^-1 (beta . dx_{t+1}).
@@ -219,6 +228,7 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
     float cur[NW], nxt[NW];
     load_block<NW>(w, cur);
     for (int64_t t = 0; t < T; ++t) {
+        if (t + SOLVE_PF < T) prefetch_block<NW>(w + (t + SOLVE_PF) * NW);
         if (t + 1 < T) load_block<NW>(w + (t + 1) * NW, nxt);
         float S[D][D], y[D], dinv[D];
 #pragma unroll
@@ -259,6 +269,10 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
 #pragma unroll
     for (int i = 0; i < D; ++i) dx[i] = u[i];
     for (int64_t t = T - 1; t >= 0; --t) {
+        if (t >= SOLVE_PF) {
+            prefetch_block<NW>(w + (t - SOLVE_PF) * NW);
+            prefetch_l1(q + (p * T + t - SOLVE_PF) * D);
+        }
         if (t < T - 1) {
             float z[D];
 #pragma unroll

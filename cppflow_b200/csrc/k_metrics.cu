@@ -72,12 +72,12 @@ path_metrics_kernel(const float* __restrict__ q, const float* __restrict__ targe
         }
         for (int pr = 0; pr < M::NPAIR; ++pr) {
             float C2[3], nrm[3];
-            d_self = fminf(d_self, self_pair_distance<M, MBLOCK>(sm, pr, C2, nrm));
+            d_self = fminf(d_self, self_pair_distance<M, MBLOCK>(sm, pr, C2, nrm, d_self));
         }
         for (int o = 0; o < ob.n; ++o)
             for (int c = 0; c < M::NCAP; ++c) {
                 float Cw[3], nrm[3];
-                d_env = fminf(d_env, env_capsule_distance<M, MBLOCK>(sm, c, ob, o, Cw, nrm));
+                d_env = fminf(d_env, env_capsule_distance<M, MBLOCK>(sm, c, ob, o, Cw, nrm, d_env));
             }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
