@@ -60,9 +60,13 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
     constexpr int NT = BlockLayout<D>::NT;
     constexpr int NW = BlockLayout<D>::NW;
     extern __shared__ float smem[];
-    const int64_t i = (int64_t)blockIdx.x * ABLOCK + threadIdx.x;
-    if (i >= P * T) return;
-    const int64_t t = i % T;
+    // consecutive threads take consecutive PATHS at the same waypoint t: the target pose is warp-uniform and the
+    // block stores below are fully coalesced in the [t][k][path] workspace layout the solve kernel streams
+    const int64_t gid = (int64_t)blockIdx.x * ABLOCK + threadIdx.x;
+    if (gid >= P * T) return;
+    const int64_t t = gid / P;
+    const int64_t pth = gid % P;
+    const int64_t i = pth * T + t;  // row of q / xv
     float* sm = smem + threadIdx.x;
 
     float x[D];
@@ -168,7 +172,7 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
 #pragma unroll
     for (int d = 0; d < D; ++d) A[tri(d, d)] += prm.lambda;
 
-    float4* out = reinterpret_cast<float4*>(ws + i * NW);
+    float4* out = reinterpret_cast<float4*>(ws) + (t * (NW / 4)) * P + pth;  // float4 k at out[k * P]
     float blk[NW];
 #pragma unroll
     for (int k = 0; k < NT; ++k) blk[k] = A[k];
@@ -177,7 +181,7 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
 #pragma unroll
     for (int k = NT + D; k < NW; ++k) blk[k] = 0.f;
 #pragma unroll
-    for (int k = 0; k < NW / 4; ++k) out[k] = make_float4(blk[4 * k], blk[4 * k + 1], blk[4 * k + 2], blk[4 * k + 3]);
+    for (int k = 0; k < NW / 4; ++k) out[k * P] = make_float4(blk[4 * k], blk[4 * k + 1], blk[4 * k + 2], blk[4 * k + 3]);
 }
 
 struct SolveParams {
@@ -201,18 +205,47 @@ __device__ __forceinline__ void store_block(float* __restrict__ p, const float (
     for (int k = 0; k < NW / 4; ++k) s[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
 }
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-template <int NW>
-__device__ __forceinline__ void prefetch_block(const float* p) {
-    prefetch_l1(p);
-    prefetch_l1(p + 32);
-    if (NW > 32) prefetch_l1(p + NW - 1);
-}
-constexpr int SOLVE_PF = 6;  // blocks prefetched ahead of the sweep (per thread, into L1)
+// ----------------------------------------------------------------------------------------------------------------
+// Block-tridiagonal solve.  Two lanes per path run a TWISTED (two-sided) block-Thomas factorisation: lane side 0
+// eliminates t = 0, 1, ... upwards, lane side 1 eliminates t = T-1, T-2, ... downwards; they meet at the middle block
+// m = T/2, whose Schur complement takes both neighbours' inverses.  This halves the sequential chain (the kernel is
+// bound by the latency of T dependent 8x8 factorisations, not by FLOPs or bandwidth).
+//   elimination (per side, "in" = the neighbour already eliminated):
+//       S_t = A_t - E S_in^-1 E,  y_t = b_t - E u_in,  u_t = S_t^-1 y_t,  E = -diag(beta);  block t <- (S_t^-1, u_t)
+//   middle:  S_m = A_m - E (S_{m-1}^-1 + S_{m+1}^-1) E,  y_m = b_m - E (u_{m-1} + u_{m+1}),  dx_m = S_m^-1 y_m
+//   back-substitution (per side, outwards from m):  dx_t = u_t + S_t^-1 (beta . dx_{inner neighbour})
+// Blocks are streamed through a per-thread ring in shared memory with cp.async (LDGSTS): the back-substitution step
+// is only ~64 FMAs, so without a deep asynchronous ring every step would expose a full DRAM round trip.
+constexpr int SOLVE_RING = 8;      // ring slots per thread
+constexpr int SOLVE_RING_FWD = 3;  // slots in flight during the elimination sweep (each step is ~1k cycles)
 
-// Block-Thomas sweep, one thread per path.  Forward: S_t = A_t - E S_{t-1}^-1 E, y_t = b_t - E u_{t-1} with
-// E = -diag(beta), u_t = S_t^-1 y_t; the workspace block is overwritten by (S_t^-1, u_t).
-// Backward: dx_t = u_t + S_t^-1 (beta . dx_{t+1}).
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int D>
+struct SolveSmem {
+    static constexpr int NV = BlockLayout<D>::NW / 4;                 // float4 per block
+    static constexpr int SLOT_BYTES = (NV * 16 + ((D + 3) / 4) * 16) * 32;  // one ring slot for the 32 lanes of the warp
+    static constexpr int BYTES = SLOT_BYTES * SOLVE_RING;
+    // float4 k of the block in `slot` for `lane`; q value d
+    __device__ static float4* blk(unsigned char* base, int slot, int k, int lane) {
+        return reinterpret_cast<float4*>(base + (size_t)slot * SLOT_BYTES) + k * 32 + lane;
+    }
+    // q value d of `lane`: groups of 4 dofs are contiguous per lane so a 16-byte cp.async can fill them
+    __device__ static float* qv(unsigned char* base, int slot, int d, int lane) {
+        return reinterpret_cast<float*>(base + (size_t)slot * SLOT_BYTES + NV * 16 * 32) + ((d >> 2) * 32 + lane) * 4 + (d & 3);
+    }
+};
+
 template <class M>
 __global__ void __launch_bounds__(32)
 lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const SolveParams prm, float* __restrict__ ws,
@@ -220,86 +253,204 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
     constexpr int D = M::NDOF;
     constexpr int NT = BlockLayout<D>::NT;
     constexpr int NW = BlockLayout<D>::NW;
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
-    float* w = ws + p * T * NW;
-    float Sinv[D][D];
-    float u[D];
-    float cur[NW], nxt[NW];
-    load_block<NW>(w, cur);
-    for (int64_t t = 0; t < T; ++t) {
-        if (t + SOLVE_PF < T) prefetch_block<NW>(w + (t + SOLVE_PF) * NW);
-        if (t + 1 < T) load_block<NW>(w + (t + 1) * NW, nxt);
-        float S[D][D], y[D], dinv[D];
+    constexpr int NV = NW / 4;
+    using SM = SolveSmem<D>;
+    extern __shared__ __align__(16) unsigned char ring[];
+    const int lane = threadIdx.x;
+    const int side = lane & 1;
+    const int64_t p_raw = (int64_t)blockIdx.x * 16 + (lane >> 1);
+    const bool active = p_raw < P;
+    const int64_t p = active ? p_raw : P - 1;  // idle lanes shadow the last path (no stores) so the warp stays converged
+    float4* w4 = reinterpret_cast<float4*>(ws) + p;  // float4 k of block t at w4[(t * NV + k) * P]
+    const float* qp = q + p * T * D;
+    const int64_t m = T / 2;
+    const int64_t n_side = side == 0 ? m : T - 1 - m;  // blocks this lane eliminates
+    const int64_t n_iter = m > T - 1 - m ? m : T - 1 - m;
+
+    auto t_of = [&](int64_t k) { return side == 0 ? k : T - 1 - k; };
+    auto issue_block = [&](int slot, int64_t t, bool with_q) {
+        const float4* src = w4 + (t * NV) * P;
 #pragma unroll
-        for (int i = 0; i < D; ++i) {
-            y[i] = cur[NT + i];
+        for (int k = 0; k < NV; ++k) cp_async16(SM::blk(ring, slot, k, lane), src + k * P);
+        if (with_q) {
+            if constexpr (D % 4 == 0) {
 #pragma unroll
-            for (int j = 0; j <= i; ++j) S[i][j] = cur[tri(i, j)];
-        }
-        if (t > 0) {
+                for (int d = 0; d < D; d += 4) cp_async16(SM::qv(ring, slot, d, lane), qp + t * D + d);
+            } else {
 #pragma unroll
-            for (int i = 0; i < D; ++i) {
-                y[i] = fmaf(prm.beta[i], u[i], y[i]);
-#pragma unroll
-                for (int j = 0; j <= i; ++j) S[i][j] = fmaf(-prm.beta[i] * prm.beta[j], Sinv[i][j], S[i][j]);
+                for (int d = 0; d < D; ++d) cp_async4(SM::qv(ring, slot, d, lane), qp + t * D + d);
             }
         }
+    };
+    auto store_blk = [&](int64_t t, const float (&v)[NW]) {
+        float4* dst = w4 + (t * NV) * P;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) dst[k * P] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    };
+    auto store_x = [&](int64_t t, const float (&xn)[D]) {
+        float* xo = x_out + (p * T + t) * D;
+        if constexpr (D % 4 == 0) {
+#pragma unroll
+            for (int d = 0; d < D; d += 4)
+                *reinterpret_cast<float4*>(xo + d) = make_float4(xn[d], xn[d + 1], xn[d + 2], xn[d + 3]);
+        } else {
+#pragma unroll
+            for (int d = 0; d < D; ++d) xo[d] = xn[d];
+        }
+    };
+    auto read_block = [&](int slot, float (&v)[NW]) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const float4 f = *SM::blk(ring, slot, k, lane);
+            v[4 * k] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w;
+        }
+    };
+
+    float Sinv[D][D];
+    float u[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        u[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) Sinv[i][j] = 0.f;
+    }
+    // factor S (lower triangle in, Cholesky), invert, u = S^-1 y
+    auto factor = [&](float (&S)[D][D], const float (&y)[D]) {
+        float dinv[D];
         chol_lower<D>(S, dinv);
         chol_inverse<D>(S, dinv, Sinv);
 #pragma unroll
         for (int i = 0; i < D; ++i) {
-            float s = 0.f;
+            float acc = 0.f;
 #pragma unroll
-            for (int j = 0; j < D; ++j) s = fmaf(j <= i ? Sinv[i][j] : Sinv[j][i], y[j], s);
-            u[i] = s;
+            for (int j = 0; j < D; ++j) acc = fmaf(j <= i ? Sinv[i][j] : Sinv[j][i], y[j], acc);
+            u[i] = acc;
+        }
+    };
+
+    // ---- elimination sweep
+#pragma unroll
+    for (int k = 0; k < SOLVE_RING_FWD; ++k) {
+        if (k < n_side) issue_block(k, t_of(k), false);
+        cp_async_commit();
+    }
+    for (int64_t k = 0; k < n_iter; ++k) {
+        cp_async_wait<SOLVE_RING_FWD - 1>();
+        if (k < n_side) {
+            const int slot = (int)(k % SOLVE_RING_FWD);
+            float blk[NW];
+            read_block(slot, blk);
+            float S[D][D], y[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                y[i] = fmaf(prm.beta[i], u[i], blk[NT + i]);  // u = 0 on the first block
+#pragma unroll
+                for (int j = 0; j <= i; ++j) S[i][j] = fmaf(-prm.beta[i] * prm.beta[j], Sinv[i][j], blk[tri(i, j)]);
+            }
+            if (k + SOLVE_RING_FWD < n_side) issue_block(slot, t_of(k + SOLVE_RING_FWD), false);
+            factor(S, y);
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                blk[NT + i] = u[i];
+#pragma unroll
+                for (int j = 0; j <= i; ++j) blk[tri(i, j)] = Sinv[i][j];
+            }
+            if (active) store_blk(t_of(k), blk);
+        }
+        cp_async_commit();
+    }
+    cp_async_wait<0>();
+
+    // ---- middle block: side 0 owns it; side 1 hands over its last (S^-1, u)
+    float dx[D];
+    {
+        float Sm[D][D], ym[D];
+        float blk[NW];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {  // both lanes of the pair read the middle block (same address)
+            const float4 f = w4[(m * NV + k) * P];
+            blk[4 * k] = f.x; blk[4 * k + 1] = f.y; blk[4 * k + 2] = f.z; blk[4 * k + 3] = f.w;
         }
 #pragma unroll
         for (int i = 0; i < D; ++i) {
-            cur[NT + i] = u[i];
+            const float uo = __shfl_xor_sync(0xffffffffu, u[i], 1);
+            ym[i] = fmaf(prm.beta[i], u[i] + uo, blk[NT + i]);
 #pragma unroll
-            for (int j = 0; j <= i; ++j) cur[tri(i, j)] = Sinv[i][j];
+            for (int j = 0; j <= i; ++j) {
+                const float so = __shfl_xor_sync(0xffffffffu, Sinv[i][j], 1);
+                Sm[i][j] = fmaf(-prm.beta[i] * prm.beta[j], Sinv[i][j] + so, blk[tri(i, j)]);
+            }
         }
-        store_block<NW>(w + t * NW, cur);
+        if (side == 0) {
+            float dinv[D], Minv[D][D];
+            chol_lower<D>(Sm, dinv);
+            chol_inverse<D>(Sm, dinv, Minv);
 #pragma unroll
-        for (int k = 0; k < NW; ++k) cur[k] = nxt[k];
+            for (int i = 0; i < D; ++i) {
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < D; ++j) acc = fmaf(j <= i ? Minv[i][j] : Minv[j][i], ym[j], acc);
+                dx[i] = acc;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) dx[i] = __shfl_sync(0xffffffffu, dx[i], lane & ~1);
+        if (side == 0 && active) {
+            float xn[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) xn[i] = __ldg(qp + m * D + i) + dx[i];
+            if (prm.do_clamp) {
+                static_for<D>([&](auto Dd) {
+                    constexpr int d = decltype(Dd)::value;
+                    xn[d] = fminf(fmaxf(xn[d], dof_lower<M>(d)), dof_upper<M>(d));
+                });
+            }
+            store_x(m, xn);
+        }
     }
-    // backward substitution
-    float dx[D];
+
+    // ---- back-substitution outwards from the middle: this lane's blocks k = n_side-1 ... 0
 #pragma unroll
-    for (int i = 0; i < D; ++i) dx[i] = u[i];
-    for (int64_t t = T - 1; t >= 0; --t) {
-        if (t >= SOLVE_PF) {
-            prefetch_block<NW>(w + (t - SOLVE_PF) * NW);
-            prefetch_l1(q + (p * T + t - SOLVE_PF) * D);
-        }
-        if (t < T - 1) {
+    for (int r = 0; r < SOLVE_RING; ++r) {
+        const int64_t k = n_side - 1 - r;
+        if (k >= 0) issue_block(r, t_of(k), true);
+        cp_async_commit();
+    }
+    for (int64_t r = 0; r < n_iter; ++r) {
+        cp_async_wait<SOLVE_RING - 1>();
+        const int64_t k = n_side - 1 - r;
+        if (k >= 0) {
+            const int slot = (int)(r % SOLVE_RING);
+            float blk[NW], qv[D];
+            read_block(slot, blk);
+#pragma unroll
+            for (int d = 0; d < D; ++d) qv[d] = *SM::qv(ring, slot, d, lane);
             float z[D];
 #pragma unroll
             for (int i = 0; i < D; ++i) z[i] = prm.beta[i] * dx[i];
 #pragma unroll
             for (int i = 0; i < D; ++i) {
-                float s = cur[NT + i];
+                float acc = blk[NT + i];
 #pragma unroll
-                for (int j = 0; j < D; ++j) s = fmaf(j <= i ? cur[tri(i, j)] : cur[tri(j, i)], z[j], s);
-                dx[i] = s;
+                for (int j = 0; j < D; ++j) acc = fmaf(j <= i ? blk[tri(i, j)] : blk[tri(j, i)], z[j], acc);
+                dx[i] = acc;
             }
-        }
-        if (t > 0) load_block<NW>(w + (t - 1) * NW, cur);  // issued before the stores below: overlaps with them
-        float xn[D];
-        const float* qp = q + (p * T + t) * D;
+            const int64_t kn = k - SOLVE_RING;
+            if (kn >= 0) issue_block(slot, t_of(kn), true);
+            float xn[D];
 #pragma unroll
-        for (int i = 0; i < D; ++i) xn[i] = __ldg(qp + i) + dx[i];
-        if (prm.do_clamp) {
-            static_for<D>([&](auto Dd) {
-                constexpr int d = decltype(Dd)::value;
-                xn[d] = fminf(fmaxf(xn[d], dof_lower<M>(d)), dof_upper<M>(d));
-            });
+            for (int i = 0; i < D; ++i) xn[i] = qv[i] + dx[i];
+            if (prm.do_clamp) {
+                static_for<D>([&](auto Dd) {
+                    constexpr int d = decltype(Dd)::value;
+                    xn[d] = fminf(fmaxf(xn[d], dof_lower<M>(d)), dof_upper<M>(d));
+                });
+            }
+            if (active) store_x(t_of(k), xn);
         }
-        float* xo = x_out + (p * T + t) * D;
-#pragma unroll
-        for (int i = 0; i < D; ++i) xo[i] = xn[i];
+        cp_async_commit();
     }
+    cp_async_wait<0>();
 }
 
 template <class M>
@@ -351,7 +502,14 @@ static int launch_solve(const cppflow_lm_params* p, const float* q, int64_t P, i
     AssembleParams ap;
     SolveParams sp;
     make_params<M>(p, 0, do_clamp, ap, sp);
-    lm_block_solve_kernel<M><<<grid_for(P, 32), 32, 0, st>>>(q, P, T, sp, ws, x_out);
+    const size_t sh = SolveSmem<M::NDOF>::BYTES;
+    static bool attr_set = false;  // per template instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(lm_block_solve_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+        if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    lm_block_solve_kernel<M><<<grid_for(P, 16), 32, sh, st>>>(q, P, T, sp, ws, x_out);
     return CPPFLOW_OK;
 }
 

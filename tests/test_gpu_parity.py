@@ -239,3 +239,32 @@ def test_full_step_vs_dense_oracle(robots, r, mode):
             assert err < max(3.0 * err_ref32, 1e-4), (p, float(err), float(err_ref32))
     if mode == "diff":
         assert n_active > 0
+
+
+@pytest.mark.parametrize("P,T", [(1, 9), (5, 10), (17, 33), (2, 301)])
+def test_full_step_shapes(robots, P, T):
+    """Twisted block solve: odd / even / minimal T (2 * n_virtual_configs < T), path counts that do not fill a warp."""
+    from cppflow_b200 import ops
+    from cppflow_b200.lm_hyper_parameters import ALT_LOSS_V2_1_DIFF
+
+    r = "fetch"
+    m, target, x0 = synthetic_problem(r, P, T, seed=11)
+    rob = robots[r]
+    cuboids, Tcuboids = cuboid_tensors(OBSTACLES[r])
+    out = ops.lm_full_step(rob.robot_id, rob.ndof, ops.make_params(ALT_LOSS_V2_1_DIFF), x0.to(DEV), None, target.to(DEV),
+                           P, T, ops.Obstacles(cuboids, Tcuboids), clamp=True).cpu()
+    ref = L.run_fixed_schedule(m, x0.double(), target.double(), "d", Tcuboids, cuboids)
+    assert (out.double() - ref).abs().max() < 1e-4
+
+
+def test_full_step_rejects_bad_arguments(robots):
+    from cppflow_b200 import ops, _lib
+    from cppflow_b200.lm_hyper_parameters import ALT_LOSS_V2_1_DIFF
+
+    rob = robots["fetch"]
+    m, target, x0 = synthetic_problem("fetch", 1, 8, seed=1)
+    with pytest.raises(_lib.CppflowError):  # 2 * n_virtual_configs (8) must be < T (optimization_utils.py:457-459)
+        ops.lm_full_step(rob.robot_id, rob.ndof, ops.make_params(ALT_LOSS_V2_1_DIFF), x0.to(DEV), None, target.to(DEV), 1, 8,
+                         None, clamp=True)
+    with pytest.raises(RuntimeError):  # CPU tensors are refused: there is no CPU fallback
+        ops.forward_kinematics(rob.robot_id, rob.ndof, x0)
