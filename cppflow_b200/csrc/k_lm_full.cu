@@ -53,7 +53,7 @@ __device__ __forceinline__ void rank1_update(float (&A)[BlockLayout<M::NDOF>::NT
 }
 
 template <class M>
-__global__ void __launch_bounds__(ABLOCK)
+__global__ void __launch_bounds__(ABLOCK, 4)
 lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, const float* __restrict__ target,
                    int64_t P, int64_t T, const Obstacles ob, const AssembleParams prm, float* __restrict__ ws) {
     constexpr int D = M::NDOF;
@@ -72,6 +72,23 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
     float x[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) x[d] = __ldg(q + i * D + d);
+    // differencing term first: its neighbour loads (uncoalesced across paths) then overlap the FK arithmetic
+    float dwrap[D];
+    const bool has_prev = t > 0, has_next = t < T - 1;
+    if (prm.use_diff) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const float wn = has_next ? wrap_pi(__ldg(q + (i + 1) * D + d) - x[d]) : 0.f;
+            const float wp = has_prev ? wrap_pi(x[d] - __ldg(q + (i - 1) * D + d)) : 0.f;
+            dwrap[d] = wn - wp;
+        }
+    }
+    float vwrap[D];
+    const bool in_virtual = prm.use_virtual && (t < prm.n_virtual || t >= T - prm.n_virtual);
+    if (in_virtual && xv) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) vwrap[d] = wrap_pi(x[d] - __ldg(xv + i * D + d));
+    }
     CollisionSink<M, ABLOCK, true> sink{sm};
     Frame F;
     fk_chain<M>(x, sink, F);
@@ -139,8 +156,8 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
         }
     }
     if (prm.use_env) {
-        for (int o = 0; o < ob.n; ++o)
-            for (int c = 0; c < M::NCAP; ++c) {
+        for (int c = 0; c < M::NCAP; ++c)
+            for (int o = 0; o < ob.n; ++o) {
                 float Cw[3], nrm[3];
                 const float d = env_capsule_distance<M, ABLOCK>(sm, c, ob, o, Cw, nrm, 0.f);
                 if (d < 0.f) {
@@ -152,21 +169,18 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
     }
 
     if (prm.use_diff) {
-        const bool has_prev = t > 0, has_next = t < T - 1;
         const float nt = (has_prev ? 1.f : 0.f) + (has_next ? 1.f : 0.f);
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            const float wn = has_next ? wrap_pi(__ldg(q + (i + 1) * D + d) - x[d]) : 0.f;
-            const float wp = has_prev ? wrap_pi(x[d] - __ldg(q + (i - 1) * D + d)) : 0.f;
-            b[d] = fmaf(prm.beta[d], wn - wp, b[d]);
+            b[d] = fmaf(prm.beta[d], dwrap[d], b[d]);
             A[tri(d, d)] = fmaf(prm.beta[d], nt, A[tri(d, d)]);
         }
     }
-    if (prm.use_virtual && (t < prm.n_virtual || t >= T - prm.n_virtual)) {
+    if (in_virtual) {
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             A[tri(d, d)] += prm.gamma2;
-            if (xv) b[d] = fmaf(-prm.gamma2, wrap_pi(x[d] - __ldg(xv + i * D + d)), b[d]);
+            if (xv) b[d] = fmaf(-prm.gamma2, vwrap[d], b[d]);
         }
     }
 #pragma unroll

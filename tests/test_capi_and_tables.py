@@ -1,0 +1,83 @@
+"""CPU: the C-ABI library loads, exports every symbol include/cppflow_b200.h declares, and its compile-time robot
+tables agree with the oracle's independently written tables.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import robots as R
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    text = open(os.path.join(REPO, "include", "cppflow_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cppflow_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported():
+    from cppflow_b200 import _lib
+
+    lib = _lib.load()
+    names = declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/cppflow_b200.h but not exported"
+    assert set(names) == set(_lib.EXPORTED_SYMBOLS), set(names) ^ set(_lib.EXPORTED_SYMBOLS)
+    assert b"sm_100a" in lib.cppflow_version()
+
+
+def test_struct_layouts_match_header():
+    from cppflow_b200 import _lib
+
+    assert ctypes.sizeof(_lib.LmParamsC) == 8 * 4 + 6 * 4
+    assert ctypes.sizeof(_lib.RobotInfoC) == 4 * 4 + 8 * 4 * 3 + 10 * 7 * 4 + 10 * 4 + 28 * 2 * 4 + 16
+
+
+def test_error_codes_without_gpu():
+    from cppflow_b200 import _lib
+
+    lib = _lib.load()
+    info = _lib.RobotInfoC()
+    assert lib.cppflow_robot_info_get(7, info) == -1  # CPPFLOW_E_INVALID
+    assert b"unknown robot id" in lib.cppflow_last_error()
+    assert lib.cppflow_lm_full_workspace_bytes(0, 8192, 300) == 8192 * 300 * 44 * 4
+    assert lib.cppflow_lm_full_workspace_bytes(2, 10, 20) == 10 * 20 * 36 * 4
+    assert lib.cppflow_dp_search_workspace_bytes(175, 295) >= 4 * (295 * 175 + 294 * 175 * 175)
+    with pytest.raises(_lib.CppflowError):
+        _lib.check(-1)
+
+
+@pytest.mark.parametrize("name", ["fetch", "fetch_arm", "panda"])
+def test_robot_tables_match_oracle(name):
+    from cppflow_b200.robot import get_robot
+    from cppflow_b200 import ops
+
+    rob = get_robot(name)
+    m = R.get_model(name)
+    assert rob.ndof == m.ndof and rob.name == m.name and rob.formal_robot_name == m.formal_robot_name
+    assert rob.prismatic_joint_idxs == m.prismatic_joint_idxs and rob.revolute_joint_idxs == m.revolute_joint_idxs
+    assert rob.actuated_joint_names == m.actuated_joint_names
+    assert rob.end_effector_link_name == m.end_effector_link_name
+    np.testing.assert_allclose(np.array(rob.actuated_joints_limits), np.array(m.actuated_joints_limits), atol=1e-6)
+    assert rob._collision_pairs == m.pairs
+    assert list(rob._collision_capsules_by_link.keys()) == [c.link for c in m.capsules]
+    info = ops._info(rob.robot_id)
+    for c, cap in enumerate(m.capsules):
+        np.testing.assert_allclose(list(info.capsules[c]), list(cap.p1) + list(cap.p2) + [cap.radius], atol=1e-7)
+        assert info.capsule_frame[c] == cap.frame
+    assert info.n_chain == len(m.chain)
+
+
+def test_no_cpu_fallback():
+    import torch
+    from cppflow_b200.robot import get_robot
+
+    rob = get_robot("panda")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rob.forward_kinematics(torch.zeros((3, 7)))
+    with pytest.raises(NotImplementedError):
+        rob.config_self_collides(None)

@@ -1,0 +1,162 @@
+"""CPU: host-side logic that does not need a GPU - parameter marshalling, validity decisions, problem loading,
+sharding, and the multi-rank cost gather over gloo (world_size 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from cppflow_b200 import ops
+from cppflow_b200.data_types import Constraints, DEFAULT_CONSTRAINTS
+from cppflow_b200.lm_hyper_parameters import ALT_LOSS_V2_1_DIFF, ALT_LOSS_V2_1_POSE, OptimizationParameters, all_terms_parameters
+
+
+def test_make_params_marshalling():
+    p = ops.make_params(ALT_LOSS_V2_1_DIFF)
+    assert (p.use_pose, p.use_differencing, p.use_virtual_configs, p.n_virtual_configs) == (0, 1, 1, 4)
+    assert (p.use_self_collisions, p.use_env_collisions) == (1, 1)
+    assert abs(p.alpha_differencing - 0.00375) < 1e-9 and abs(p.lm_lambda - 1e-6) < 1e-12 and p.alpha_position == 0.0
+    p = ops.make_params(ALT_LOSS_V2_1_POSE)
+    assert (p.use_pose, p.use_differencing, p.use_virtual_configs, p.n_virtual_configs) == (1, 0, 0, 0)
+    assert (p.alpha_position, p.alpha_rotation) == (3.5, pytest.approx(0.35))
+    p = ops.make_params(all_terms_parameters())
+    assert p.use_pose == 1 and p.use_differencing == 1 and p.use_self_collisions == 1
+    bad = OptimizationParameters(**{**ALT_LOSS_V2_1_DIFF.__dict__, "differencing_do_scale_satisfied": True,
+                                    "differencing_ignore_satisfied_margin_deg": 1.0,
+                                    "differencing_ignore_satisfied_margin_cm": 1.0})
+    with pytest.raises(NotImplementedError):
+        ops.make_params(bad)
+
+
+def test_obstacle_tables():
+    c = torch.tensor([-0.1, -0.2, -0.3, 0.1, 0.2, 0.3])
+    T = torch.zeros((4, 4))
+    T[:3, :3] = torch.eye(3)
+    T[:3, 3] = torch.tensor([1.0, 2.0, 3.0])
+    ob = ops.Obstacles([c, c], [T, T])
+    assert ob.n == 2 and list(ob.cuboids_ptr)[:6] == pytest.approx(c.tolist())
+    assert list(ob.Tcuboids_ptr)[3] == 1.0 and list(ob.single(1).Tcuboids_ptr)[7] == 2.0
+    assert ops._obs(None) == (None, None, 0) and ops._obs(ops.Obstacles()) == (None, None, 0)
+    with pytest.raises(AssertionError):
+        ops.Obstacles([c] * 9, [T] * 9)
+
+
+class _FakeRobot:
+    ndof, robot_id, name, formal_robot_name = 8, 0, "fetch", "Fetch"
+
+
+def _problem(T=10):
+    from cppflow_b200.data_types import Problem
+
+    tp = torch.zeros((T, 7))
+    tp[:, 3] = 1.0
+    return Problem(DEFAULT_CONSTRAINTS, tp, None, _FakeRobot(), "t", "t", [], [], [], [])
+
+
+def test_x_is_valid_decisions():
+    """optimization_utils.py:836-923: first path passing every threshold and the collision check wins."""
+    from cppflow_b200.optimization_utils import x_is_valid
+
+    prob = _problem()
+    x = torch.arange(3 * 10 * 8, dtype=torch.float32).reshape(30, 8)
+    #            pos_cm rot_deg mjac_deg mjac_cm tl  min_self min_env pad
+    metrics = torch.tensor([[0.5, 0.01, 1.0, 0.1, 3.0, 0.1, 0.1, 0],      # position error too large
+                            [0.001, 0.01, 1.0, 0.1, 3.0, -0.01, 0.1, 0],  # self collision
+                            [0.001, 0.01, 1.0, 0.1, 3.0, 0.02, 0.03, 0]])
+    x_sol, idx, flags = x_is_valid(prob, DEFAULT_CONSTRAINTS, None, x, 3, metrics=metrics)
+    assert idx == 2 and torch.equal(x_sol, x[20:30]) and flags == (True, True, True, True, False, False)
+    x_sol, idx, flags = x_is_valid(prob, DEFAULT_CONSTRAINTS, None, x[:20], 2, metrics=metrics[:2])
+    assert x_sol is None and idx is None and flags[4] is True
+    x_sol, idx, flags = x_is_valid(prob, DEFAULT_CONSTRAINTS, None, x[:10], 1, metrics=metrics[:1])
+    assert x_sol is None and flags[:4] == (False, True, True, True) and flags[4] is None
+    # thresholds are strict '<' (evaluation_utils.py:41-58)
+    edge = torch.tensor([[0.5, 0.01, 1.0, 0.1, 3.0, 0.1, 0.1, 0]])
+    assert x_is_valid(prob, Constraints(0.5, 0.1, 7.0, 2.0), None, x[:10], 1, metrics=edge)[0] is None
+    assert x_is_valid(prob, Constraints(0.5001, 0.1, 7.0, 2.0), None, x[:10], 1, metrics=edge)[0] is not None
+    # a mesh-level validator (klampt in the reference) overrides the capsule verdict
+    x_sol, _, flags = x_is_valid(prob, DEFAULT_CONSTRAINTS, None, x[:20], 2, metrics=metrics[:2],
+                                 mesh_validator=lambda p, xi: (False, False))
+    assert x_sol is not None and flags[4] is False
+
+
+def test_problem_loader_matches_reference_files():
+    """data_type_utils.py:148-219 / SURVEY 8d config 4: 13 benchmark problems, sum T = 4036."""
+    from cppflow_b200.data_type_utils import ALL_PROBLEM_FILENAMES, problem_from_filename
+
+    expected_T = {"hello": 553, "circle": 295, "rot_yz2": 249, "s": 301, "square": 320, "1cube": 200, "2cubes": 200,
+                  "flappy_bird": 200}
+    total = 0
+    for name in ALL_PROBLEM_FILENAMES:
+        p = problem_from_filename(None, name, device="cpu")
+        assert p.n_timesteps == expected_T[p.name] and p.target_path.shape == (p.n_timesteps, 7)
+        assert torch.allclose(p.target_path[:, 3:].norm(dim=1), torch.ones(p.n_timesteps), atol=1e-3)
+        assert len(p.obstacles_cuboids) == len(p.obstacles_Tcuboids) == p.obstacle_tables.n
+        total += p.n_timesteps
+    assert total == 4036
+    p = problem_from_filename(None, "fetch__circle", device="cpu")
+    # problems/fetch__circle.yaml: offset (0.9, 0.25, 0.46) from torso_lift_link at q = 0
+    np.testing.assert_allclose(p.target_path[0, :3].numpy(), [0.9 - 0.086875, 0.25, 0.46 + 0.37743], atol=1e-6)
+    assert p.obstacles_cuboids[0].tolist() == pytest.approx([-0.15, -0.025, -0.4, 0.15, 0.025, 0.4])
+    assert p.obstacles_Tcuboids[2][:3, 3].tolist() == pytest.approx([0.4, 0.0, 1.225]) and p.obstacles_Tcuboids[0][3, 3] == 0
+    p = problem_from_filename(None, "fetch__s", device="cpu")  # obstacle_xyz_offset (0, 0, -0.2)
+    assert p.obstacles_Tcuboids[0][2, 3].item() == pytest.approx(0.36 - 0.2)
+    with pytest.raises(ValueError):
+        from cppflow_b200.data_types import Problem
+
+        Problem(DEFAULT_CONSTRAINTS, torch.zeros((4, 7)), None, _FakeRobot(), "bad", "bad", [], [], [], [])
+
+
+def test_shard_range_and_costs():
+    from cppflow_b200.distributed import shard_range, path_costs, INVALID_COST
+
+    for n, w in [(8192, 8), (13, 4), (3, 8)]:
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(e - s for s, e in spans) - min(e - s for s, e in spans) <= 1
+    m = torch.tensor([[0.001, 0.01, 1.0, 0.1, 3.0, 0.1, 0.1, 0], [0.5, 0.01, 1.0, 0.1, 2.0, 0.1, 0.1, 0],
+                      [0.001, 0.01, 1.0, 0.1, 2.5, 0.1, -0.1, 0]])
+    c = path_costs(m, DEFAULT_CONSTRAINTS)
+    assert c.tolist() == pytest.approx([3.0, 2.0 + INVALID_COST, 2.5 + INVALID_COST])
+
+
+def _gather_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from cppflow_b200.distributed import gather_costs_and_argmin, shard_range
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    P = 37
+    metrics = torch.zeros((P, 8))
+    metrics[:, 4] = torch.rand(P, generator=g) + 1.0  # trajectory lengths
+    metrics[:, 5:7] = 0.1
+    metrics[5, 4] = metrics[29, 4] = 0.5              # tie across shards -> lowest global index wins
+    s, e = shard_range(P, rank, world)
+    best = gather_costs_and_argmin(metrics[s:e], DEFAULT_CONSTRAINTS, rank, world)
+    out[rank] = (best, (s, e))
+    dist.destroy_process_group()
+
+
+def test_gather_argmin_two_ranks_gloo():
+    """the argmin is invariant to the shard count."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_gather_worker, args=(2, port, out), nprocs=2, join=True)
+    (b0, span0), (b1, span1) = out[0], out[1]
+    assert b0 == b1
+    cost, rank, idx = b0
+    assert cost == pytest.approx(0.5) and rank == 0 and span0[0] + idx == 5
+    from cppflow_b200.distributed import gather_costs_and_argmin
+
+    g = torch.Generator().manual_seed(0)
+    metrics = torch.zeros((37, 8))
+    metrics[:, 4] = torch.rand(37, generator=g) + 1.0
+    metrics[:, 5:7] = 0.1
+    metrics[5, 4] = metrics[29, 4] = 0.5
+    assert gather_costs_and_argmin(metrics, DEFAULT_CONSTRAINTS, 0, 1) == (pytest.approx(0.5), 0, 5)
