@@ -250,4 +250,255 @@ __device__ __forceinline__ void env_capsule_gradient(const float* sm, int c, con
     });
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------
+// Two-phase active-set evaluation (used where only the SIGN of a distance matters: the collision flags, the LM
+// assembly and the validity metrics).
+//   phase 1: every pair is tested against its conservative bounding-sphere bound with the capsule midpoints held in
+//            registers, fully unrolled (compile-time pair table, ~9 instructions per pair) -> bitmask of survivors;
+//   phase 2: `while (mask)` over the survivors with a runtime pair index: exact closed-form distance from the
+//            endpoints in the thread's shared-memory column.  Lanes of a warp walk their own survivor lists in
+//            lock-step, so a warp pays max-over-lanes(#survivors) evaluations, not the union.
+// Tables indexed by a per-lane runtime index live in shared memory (divergent constant-bank reads serialise).
+
+template <class M>
+struct CollTables {
+    int pair_ab[M::NPAIR];      // a | b << 8 | frame(a) << 16 | frame(b) << 24
+    float pair_rsum[M::NPAIR];
+    int cap_frame[M::NCAP];
+    float cap_radius[M::NCAP];
+    Obstacles ob;
+};
+
+template <class M>
+__device__ __forceinline__ void fill_coll_tables(CollTables<M>& tb, const Obstacles& ob, int tid, int nthreads) {
+    for (int p = tid; p < M::NPAIR; p += nthreads) {
+        tb.pair_ab[p] = c_pair_table<M>.a[p] | (c_pair_table<M>.b[p] << 8) | (c_pair_table<M>.fa[p] << 16) |
+                        (c_pair_table<M>.fb[p] << 24);
+        tb.pair_rsum[p] = c_pair_table<M>.rsum[p];
+    }
+    for (int c = tid; c < M::NCAP; c += nthreads) {
+        tb.cap_frame[c] = c_cap_table<M>.frame[c];
+        tb.cap_radius[c] = c_cap_table<M>.radius[c];
+    }
+    const int* src = reinterpret_cast<const int*>(&ob);
+    int* dst = reinterpret_cast<int*>(&tb.ob);
+    for (int k = tid; k < (int)(sizeof(Obstacles) / sizeof(int)); k += nthreads) dst[k] = src[k];
+}
+
+// FK sink that additionally keeps TWICE the capsule midpoints (P + Q) in registers for the unrolled culls
+template <class M, int BLOCK, bool WITH_JOINTS>
+struct MidSink {
+    float* sm;
+    float mid2[M::NCAP][3];
+    template <int D>
+    __device__ __forceinline__ void joint(std::integral_constant<int, D>, const float* axis, const float* origin) {
+        if constexpr (WITH_JOINTS) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                sm[(SmemLayout<M>::JOINTS + D * 6 + r) * BLOCK] = axis[r];
+                sm[(SmemLayout<M>::JOINTS + D * 6 + 3 + r) * BLOCK] = origin[r];
+            }
+        }
+    }
+    template <int F>
+    __device__ __forceinline__ void frame(std::integral_constant<int, F>, const Frame& fr) {
+        static_for<M::NCAP>([&](auto Cc) {
+            constexpr int c = decltype(Cc)::value;
+            if constexpr (M::cap_frame(c) == F) {
+                float P[3], Q[3];
+                capsule_endpoint<M, c, 0>(fr, P);
+                capsule_endpoint<M, c, 1>(fr, Q);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    sm[(c * 6 + r) * BLOCK] = P[r];
+                    sm[(c * 6 + 3 + r) * BLOCK] = Q[r];
+                    mid2[c][r] = P[r] + Q[r];
+                }
+            }
+        });
+    }
+};
+
+template <class M>
+__host__ __device__ constexpr float pair_reach(int p) {
+    const int a = pair_cap<M>(p, 0), b = pair_cap<M>(p, 1);
+    return M::cap(a, 6) + M::cap(b, 6) + cap_half_length<M>(a) + cap_half_length<M>(b) + CPPFLOW_CULL_MARGIN;
+}
+template <class M>
+__host__ __device__ constexpr float cap_reach(int c) {
+    return M::cap(c, 6) + cap_half_length<M>(c) + CPPFLOW_CULL_MARGIN;
+}
+
+// bit p set <=> self-collision pair p may have distance <= 0 (not proven apart by the bounding spheres)
+template <class M>
+__device__ __forceinline__ unsigned self_cull_mask(const float (&mid2)[M::NCAP][3]) {
+    static_assert(M::NPAIR <= 32, "pair mask is 32 bits");
+    unsigned mask = 0u;
+    static_for<M::NPAIR>([&](auto Pp) {
+        constexpr int p = decltype(Pp)::value;
+        constexpr int a = pair_cap<M>(p, 0), b = pair_cap<M>(p, 1);
+        constexpr float lim = pair_reach<M>(p);
+        constexpr float lim2x4 = 4.f * lim * lim;  // the midpoints are doubled
+        const float mx = mid2[a][0] - mid2[b][0], my = mid2[a][1] - mid2[b][1], mz = mid2[a][2] - mid2[b][2];
+        const float dd = fmaf(mz, mz, fmaf(my, my, mx * mx));
+        mask |= (dd > lim2x4) ? 0u : (1u << p);
+    });
+    return mask;
+}
+
+// bit c set <=> capsule c may touch obstacle o
+template <class M>
+__device__ __forceinline__ unsigned env_cull_mask(const float (&mid2)[M::NCAP][3], const Obstacles& ob, int o) {
+    unsigned mask = 0u;
+    const float t2[3] = {2.f * ob.t[o][0], 2.f * ob.t[o][1], 2.f * ob.t[o][2]};
+    const float lo2[3] = {2.f * ob.lo[o][0], 2.f * ob.lo[o][1], 2.f * ob.lo[o][2]};
+    const float hi2[3] = {2.f * ob.hi[o][0], 2.f * ob.hi[o][1], 2.f * ob.hi[o][2]};
+    if (ob.has_rot[o]) {
+        static_for<M::NCAP>([&](auto Cc) {
+            constexpr int c = decltype(Cc)::value;
+            constexpr float lim = cap_reach<M>(c);
+            constexpr float lim2x4 = 4.f * lim * lim;
+            const float v[3] = {mid2[c][0] - t2[0], mid2[c][1] - t2[1], mid2[c][2] - t2[2]};
+            float dd = 0.f;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float m = fmaf(ob.R[o][6 + r], v[2], fmaf(ob.R[o][3 + r], v[1], ob.R[o][r] * v[0]));
+                const float e = m - fminf(fmaxf(m, lo2[r]), hi2[r]);
+                dd = fmaf(e, e, dd);
+            }
+            mask |= (dd > lim2x4) ? 0u : (1u << c);
+        });
+    } else {
+        const float wlo[3] = {lo2[0] + t2[0], lo2[1] + t2[1], lo2[2] + t2[2]};
+        const float whi[3] = {hi2[0] + t2[0], hi2[1] + t2[1], hi2[2] + t2[2]};
+        static_for<M::NCAP>([&](auto Cc) {
+            constexpr int c = decltype(Cc)::value;
+            constexpr float lim = cap_reach<M>(c);
+            constexpr float lim2x4 = 4.f * lim * lim;
+            float dd = 0.f;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float e = mid2[c][r] - fminf(fmaxf(mid2[c][r], wlo[r]), whi[r]);
+                dd = fmaf(e, e, dd);
+            }
+            mask |= (dd > lim2x4) ? 0u : (1u << c);
+        });
+    }
+    return mask;
+}
+
+// exact signed distance of pair p (runtime index; tables from shared memory); C2 / nrm as in self_pair_distance
+template <class M, int BLOCK>
+__device__ __forceinline__ float self_pair_exact(const float* sm, const CollTables<M>& tb, int p, float (&C2)[3],
+                                                 float (&nrm)[3]) {
+    const int ab = tb.pair_ab[p];
+    float P1[3], Q1[3], P2[3], Q2[3];
+    load_capsule<BLOCK>(sm, ab & 0xff, P1, Q1);
+    load_capsule<BLOCK>(sm, (ab >> 8) & 0xff, P2, Q2);
+    float s, t;
+    segseg_closest(P1, Q1, P2, Q2, s, t);
+    float diff[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float c1 = fmaf(s, Q1[r] - P1[r], P1[r]);
+        C2[r] = fmaf(t, Q2[r] - P2[r], P2[r]);
+        diff[r] = c1 - C2[r];
+    }
+    const float d2 = dot3(diff, diff);
+    const float dist = sqrtf(d2);
+    const float inv = d2 > 1e-24f ? rsqrtf(d2) : 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) nrm[r] = diff[r] * inv;
+    return dist - tb.pair_rsum[p];
+}
+
+template <class M, int BLOCK>
+__device__ __forceinline__ void self_pair_gradient_rt(const float* sm, const CollTables<M>& tb, int p,
+                                                      const float (&C2)[3], const float (&nrm)[3], float (&g)[M::NDOF]) {
+    const int ab = tb.pair_ab[p];
+    const int fa = (ab >> 16) & 0xff, fb = (ab >> 24) & 0xff;
+    static_for<M::NDOF>([&](auto Dd) {
+        constexpr int d = decltype(Dd)::value;
+        constexpr int ci = chain_of_dof<M>(d);
+        float gd = 0.f;
+        if (ci >= fa && ci < fb) {
+            float a[3], o[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                a[r] = sm[(SmemLayout<M>::JOINTS + d * 6 + r) * BLOCK];
+                o[r] = sm[(SmemLayout<M>::JOINTS + d * 6 + 3 + r) * BLOCK];
+            }
+            if constexpr (dof_is_prismatic<M>(d)) {
+                gd = -dot3(nrm, a);
+            } else {
+                const float rr[3] = {C2[0] - o[0], C2[1] - o[1], C2[2] - o[2]};
+                float v[3];
+                cross3(a, rr, v);
+                gd = -dot3(nrm, v);
+            }
+        }
+        g[d] = gd;
+    });
+}
+
+template <class M, int BLOCK>
+__device__ __forceinline__ float env_capsule_exact(const float* sm, const CollTables<M>& tb, int c, int o,
+                                                   float (&Cw)[3], float (&nrm)[3]) {
+    const Obstacles& ob = tb.ob;
+    float P[3], Q[3], A[3], B[3];
+    load_capsule<BLOCK>(sm, c, P, Q);
+    to_box_frame(ob, o, P, A);
+    to_box_frame(ob, o, Q, B);
+    const float t = segbox_closest(A, B, ob.lo[o], ob.hi[o]);
+    float diff[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float cb = fmaf(t, B[r] - A[r], A[r]);
+        diff[r] = cb - fminf(fmaxf(cb, ob.lo[o][r]), ob.hi[o][r]);
+        Cw[r] = fmaf(t, Q[r] - P[r], P[r]);
+    }
+    const float d2 = dot3(diff, diff);
+    const float dist = sqrtf(d2);
+    const float inv = d2 > 1e-24f ? rsqrtf(d2) : 0.f;
+    const float nb[3] = {diff[0] * inv, diff[1] * inv, diff[2] * inv};
+    if (ob.has_rot[o]) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            nrm[r] = fmaf(ob.R[o][3 * r + 2], nb[2], fmaf(ob.R[o][3 * r + 1], nb[1], ob.R[o][3 * r] * nb[0]));
+    } else {
+        nrm[0] = nb[0]; nrm[1] = nb[1]; nrm[2] = nb[2];
+    }
+    return dist - tb.cap_radius[c];
+}
+
+template <class M, int BLOCK>
+__device__ __forceinline__ void env_capsule_gradient_rt(const float* sm, const CollTables<M>& tb, int c,
+                                                        const float (&Cw)[3], const float (&nrm)[3],
+                                                        float (&g)[M::NDOF]) {
+    const int fc = tb.cap_frame[c];
+    static_for<M::NDOF>([&](auto Dd) {
+        constexpr int d = decltype(Dd)::value;
+        constexpr int ci = chain_of_dof<M>(d);
+        float gd = 0.f;
+        if (ci < fc) {
+            float a[3], o[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                a[r] = sm[(SmemLayout<M>::JOINTS + d * 6 + r) * BLOCK];
+                o[r] = sm[(SmemLayout<M>::JOINTS + d * 6 + 3 + r) * BLOCK];
+            }
+            if constexpr (dof_is_prismatic<M>(d)) {
+                gd = dot3(nrm, a);
+            } else {
+                const float rr[3] = {Cw[0] - o[0], Cw[1] - o[1], Cw[2] - o[2]};
+                float v[3];
+                cross3(a, rr, v);
+                gd = dot3(nrm, v);
+            }
+        }
+        g[d] = gd;
+    });
+}
+
 }  // namespace cppflow

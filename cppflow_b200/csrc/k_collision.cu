@@ -75,30 +75,49 @@ __global__ void __launch_bounds__(CBLOCK)
 collision_flags_kernel(const float* __restrict__ q, int64_t n, const Obstacles ob, uint8_t* __restrict__ self_flags,
                        uint8_t* __restrict__ env_flags) {
     extern __shared__ float smem[];
-    const int64_t i = (int64_t)blockIdx.x * CBLOCK + threadIdx.x;
-    if (i >= n) return;
+    __shared__ CollTables<M> tb;
+    fill_coll_tables<M>(tb, ob, threadIdx.x, CBLOCK);
+    const int64_t i_raw = (int64_t)blockIdx.x * CBLOCK + threadIdx.x;
+    const bool live = i_raw < n;
+    const int64_t i = live ? i_raw : n - 1;
     float* sm = smem + threadIdx.x;
     float x[M::NDOF];
     load_q_plain<M>(q, i, x);
-    CollisionSink<M, CBLOCK, false> sink{sm};
+    __syncthreads();
+    MidSink<M, CBLOCK, false> sink;
+    sink.sm = sm;
     Frame F;
     fk_chain<M>(x, sink, F);
+    // only the sign of the minimum matters: bounding-sphere culls in registers, exact distance for the survivors
     if (self_flags) {
-        float dmin = INFINITY;
-        for (int p = 0; p < M::NPAIR; ++p) {
+        unsigned mask = self_cull_mask<M>(sink.mid2);
+        bool hit = false;
+        while (mask) {
+            const int p = __ffs(mask) - 1;
+            mask &= mask - 1;
             float C2[3], nrm[3];
-            dmin = fminf(dmin, self_pair_distance<M, CBLOCK>(sm, p, C2, nrm, 0.f));
+            if (self_pair_exact<M, CBLOCK>(sm, tb, p, C2, nrm) < 0.f) {
+                hit = true;
+                mask = 0u;
+            }
         }
-        self_flags[i] = dmin < 0.f ? 1 : 0;
+        if (live) self_flags[i] = hit ? 1 : 0;
     }
     if (env_flags) {
-        float dmin = INFINITY;
-        for (int o = 0; o < ob.n; ++o)
-            for (int c = 0; c < M::NCAP; ++c) {
+        bool hit = false;
+        for (int o = 0; o < tb.ob.n; ++o) {
+            unsigned mask = hit ? 0u : env_cull_mask<M>(sink.mid2, tb.ob, o);
+            while (mask) {
+                const int c = __ffs(mask) - 1;
+                mask &= mask - 1;
                 float Cw[3], nrm[3];
-                dmin = fminf(dmin, env_capsule_distance<M, CBLOCK>(sm, c, ob, o, Cw, nrm, 0.f));
+                if (env_capsule_exact<M, CBLOCK>(sm, tb, c, o, Cw, nrm) < 0.f) {
+                    hit = true;
+                    mask = 0u;
+                }
             }
-        env_flags[i] = dmin < 0.f ? 1 : 0;
+        }
+        if (live) env_flags[i] = hit ? 1 : 0;
     }
 }
 

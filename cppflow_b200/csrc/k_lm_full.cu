@@ -52,44 +52,75 @@ __device__ __forceinline__ void rank1_update(float (&A)[BlockLayout<M::NDOF>::NT
     }
 }
 
+// one q row -> registers; 16-byte vector loads when the row is 16-byte aligned (D % 4 == 0)
+template <int D>
+__device__ __forceinline__ void load_row(const float* __restrict__ p, float (&x)[D]) {
+    if constexpr (D % 4 == 0) {
+#pragma unroll
+        for (int d = 0; d < D; d += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p + d));
+            x[d] = v.x; x[d + 1] = v.y; x[d + 2] = v.z; x[d + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d) x[d] = __ldg(p + d);
+    }
+}
+
+// wrap to [-pi, pi) for the LM residuals (evaluation_utils.py:144-154): one rounding step instead of fmodf.  Within
+// 1 ulp of torch.remainder for |d| < 4 pi (joint differences are < 2 pi); the bit-exact wrap_pi stays in dp_search.
+__device__ __forceinline__ float wrap_pi_lm(float d) {
+    const float k = floorf(fmaf(d, 0.15915494309189535f, 0.5f));
+    return fmaf(k, -6.28318548202514648f, d);  // float32(2 pi), the modulus torch uses
+}
+
 template <class M>
 __global__ void __launch_bounds__(ABLOCK, 4)
 lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, const float* __restrict__ target,
-                   int64_t P, int64_t T, const Obstacles ob, const AssembleParams prm, float* __restrict__ ws) {
+                   int P, int T, const Obstacles ob, const AssembleParams prm, float* __restrict__ ws) {
     constexpr int D = M::NDOF;
     constexpr int NT = BlockLayout<D>::NT;
     constexpr int NW = BlockLayout<D>::NW;
     extern __shared__ float smem[];
-    // consecutive threads take consecutive PATHS at the same waypoint t: the target pose is warp-uniform and the
-    // block stores below are fully coalesced in the [t][k][path] workspace layout the solve kernel streams
-    const int64_t gid = (int64_t)blockIdx.x * ABLOCK + threadIdx.x;
-    if (gid >= P * T) return;
-    const int64_t t = gid / P;
-    const int64_t pth = gid % P;
-    const int64_t i = pth * T + t;  // row of q / xv
+    __shared__ CollTables<M> tb;
+    fill_coll_tables<M>(tb, ob, threadIdx.x, ABLOCK);
+    // grid = (path blocks, waypoints): consecutive threads take consecutive PATHS at the same waypoint t, so the
+    // target pose is block-uniform and the block stores below are fully coalesced in the [t][k][path] workspace
+    const int t = blockIdx.y;
+    const int pth_raw = blockIdx.x * ABLOCK + threadIdx.x;
+    const bool live = pth_raw < P;
+    const int pth = live ? pth_raw : P - 1;  // idle lanes shadow the last path and skip the stores
+    const int64_t i = (int64_t)pth * T + t;  // row of q / xv
     float* sm = smem + threadIdx.x;
 
-    float x[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) x[d] = __ldg(q + i * D + d);
-    // differencing term first: its neighbour loads (uncoalesced across paths) then overlap the FK arithmetic
-    float dwrap[D];
+    // all global loads up front (the neighbour rows are strided across paths, like the row itself); the wrapped
+    // differences are formed right away so that only D of the 3 D neighbour values stay live through the FK
+    float x[D], dwrap[D], vwrap[D];
     const bool has_prev = t > 0, has_next = t < T - 1;
-    if (prm.use_diff) {
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            const float wn = has_next ? wrap_pi(__ldg(q + (i + 1) * D + d) - x[d]) : 0.f;
-            const float wp = has_prev ? wrap_pi(x[d] - __ldg(q + (i - 1) * D + d)) : 0.f;
-            dwrap[d] = wn - wp;
-        }
-    }
-    float vwrap[D];
     const bool in_virtual = prm.use_virtual && (t < prm.n_virtual || t >= T - prm.n_virtual);
-    if (in_virtual && xv) {
+    load_row<D>(q + i * D, x);
+    float tg[7];
+    if (prm.use_pose) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) vwrap[d] = wrap_pi(x[d] - __ldg(xv + i * D + d));
+        for (int k = 0; k < 7; ++k) tg[k] = __ldg(target + (int64_t)t * 7 + k);
     }
-    CollisionSink<M, ABLOCK, true> sink{sm};
+    if (prm.use_diff) {
+        float xp[D], xn[D];
+        load_row<D>(q + (has_prev ? i - 1 : i) * D, xp);
+        load_row<D>(q + (has_next ? i + 1 : i) * D, xn);
+#pragma unroll
+        for (int d = 0; d < D; ++d) dwrap[d] = wrap_pi_lm(xn[d] - x[d]) - wrap_pi_lm(x[d] - xp[d]);  // 0 at the ends
+    }
+    if (in_virtual && xv) {
+        float xvv[D];
+        load_row<D>(xv + i * D, xvv);
+#pragma unroll
+        for (int d = 0; d < D; ++d) vwrap[d] = wrap_pi_lm(x[d] - xvv[d]);
+    }
+    __syncthreads();  // collision tables visible
+
+    MidSink<M, ABLOCK, true> sink;
+    sink.sm = sm;
     Frame F;
     fk_chain<M>(x, sink, F);
 
@@ -99,11 +130,47 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
 #pragma unroll
     for (int d = 0; d < D; ++d) b[d] = 0.f;
 
-    if (prm.use_pose) {
-        float tg[7];
-        const float* tp = target + t * 7;
+    // ---- capsule collisions: register culls -> survivor masks -> exact distance; d < 0 adds w^2 g g^T, -w^2 d g
+    if (prm.use_self) {
+        unsigned mask = self_cull_mask<M>(sink.mid2);
+        while (mask) {
+            const int p = __ffs(mask) - 1;
+            mask &= mask - 1;
+            float C2[3], nrm[3];
+            const float d = self_pair_exact<M, ABLOCK>(sm, tb, p, C2, nrm);
+            if (d < 0.f) {  // residual -alpha d > 0 (optimization_utils.py:653-660)
+                float g[D];
+                self_pair_gradient_rt<M, ABLOCK>(sm, tb, p, C2, nrm, g);
+                rank1_update<M>(A, b, g, prm.w2_self, d);
+            }
+        }
+    }
+    if (prm.use_env) {
+        // survivors of up to three obstacles share one 32-bit mask (bit = oo * NCAP + c) so that the lanes of a warp
+        // walk lists of similar length
+        constexpr int OGRP = 32 / M::NCAP;
+        for (int o0 = 0; o0 < tb.ob.n; o0 += OGRP) {
+            unsigned mask = 0u;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) tg[k] = __ldg(tp + k);
+            for (int oo = 0; oo < OGRP; ++oo)
+                if (o0 + oo < tb.ob.n) mask |= env_cull_mask<M>(sink.mid2, tb.ob, o0 + oo) << (oo * M::NCAP);
+            while (mask) {
+                const int bit = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int oo = bit / M::NCAP, c = bit - oo * M::NCAP;
+                float Cw[3], nrm[3];
+                const float d = env_capsule_exact<M, ABLOCK>(sm, tb, c, o0 + oo, Cw, nrm);
+                if (d < 0.f) {
+                    float g[D];
+                    env_capsule_gradient_rt<M, ABLOCK>(sm, tb, c, Cw, nrm, g);
+                    rank1_update<M>(A, b, g, prm.w2_env, d);
+                }
+            }
+        }
+    }
+
+    // ---- pose term: Jp^T Jp, Jp^T e with the alpha-scaled geometric Jacobian (optimization.py:77-87)
+    if (prm.use_pose) {
         float e[6];
         pose_error(tg, F, e);
         float J[6][D];
@@ -128,44 +195,22 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
         });
 #pragma unroll
         for (int r = 0; r < 3; ++r) { e[r] *= prm.a_rot; e[r + 3] *= prm.a_pos; }
+        static_for<D>([&](auto Cc) {
+            constexpr int c = decltype(Cc)::value;
+            constexpr int r0c = dof_is_prismatic<M>(c) ? 3 : 0;  // rows 0-2 of a prismatic column are zero
+            float s = b[c];
 #pragma unroll
-        for (int c = 0; c < D; ++c) {
-            float s = 0.f;
-#pragma unroll
-            for (int r = 0; r < 6; ++r) s = fmaf(J[r][c], e[r], s);
+            for (int r = r0c; r < 6; ++r) s = fmaf(J[r][c], e[r], s);
             b[c] = s;
+            static_for<c + 1>([&](auto C2c) {
+                constexpr int c2 = decltype(C2c)::value;
+                constexpr int r0 = (dof_is_prismatic<M>(c) || dof_is_prismatic<M>(c2)) ? 3 : 0;
+                float v = A[tri(c, c2)];
 #pragma unroll
-            for (int c2 = 0; c2 <= c; ++c2) {
-                float v = 0.f;
-#pragma unroll
-                for (int r = 0; r < 6; ++r) v = fmaf(J[r][c], J[r][c2], v);
+                for (int r = r0; r < 6; ++r) v = fmaf(J[r][c], J[r][c2], v);
                 A[tri(c, c2)] = v;
-            }
-        }
-    }
-
-    if (prm.use_self) {
-        for (int p = 0; p < M::NPAIR; ++p) {
-            float C2[3], nrm[3];
-            const float d = self_pair_distance<M, ABLOCK>(sm, p, C2, nrm, 0.f);
-            if (d < 0.f) {  // residual -alpha d > 0 (optimization_utils.py:653-660)
-                float g[D];
-                self_pair_gradient<M, ABLOCK>(sm, p, C2, nrm, g);
-                rank1_update<M>(A, b, g, prm.w2_self, d);
-            }
-        }
-    }
-    if (prm.use_env) {
-        for (int c = 0; c < M::NCAP; ++c)
-            for (int o = 0; o < ob.n; ++o) {
-                float Cw[3], nrm[3];
-                const float d = env_capsule_distance<M, ABLOCK>(sm, c, ob, o, Cw, nrm, 0.f);
-                if (d < 0.f) {
-                    float g[D];
-                    env_capsule_gradient<M, ABLOCK>(sm, c, Cw, nrm, g);
-                    rank1_update<M>(A, b, g, prm.w2_env, d);
-                }
-            }
+            });
+        });
     }
 
     if (prm.use_diff) {
@@ -186,7 +231,8 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
 #pragma unroll
     for (int d = 0; d < D; ++d) A[tri(d, d)] += prm.lambda;
 
-    float4* out = reinterpret_cast<float4*>(ws) + (t * (NW / 4)) * P + pth;  // float4 k at out[k * P]
+    if (!live) return;
+    float4* out = reinterpret_cast<float4*>(ws) + ((int64_t)t * (NW / 4)) * P + pth;  // float4 k at out[k * P]
     float blk[NW];
 #pragma unroll
     for (int k = 0; k < NT; ++k) blk[k] = A[k];
@@ -195,7 +241,7 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
 #pragma unroll
     for (int k = NT + D; k < NW; ++k) blk[k] = 0.f;
 #pragma unroll
-    for (int k = 0; k < NW / 4; ++k) out[k * P] = make_float4(blk[4 * k], blk[4 * k + 1], blk[4 * k + 2], blk[4 * k + 3]);
+    for (int k = 0; k < NW / 4; ++k) out[(int64_t)k * P] = make_float4(blk[4 * k], blk[4 * k + 1], blk[4 * k + 2], blk[4 * k + 3]);
 }
 
 struct SolveParams {
@@ -506,7 +552,8 @@ static int launch_assemble(const cppflow_lm_params* p, const float* q, const flo
         if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    lm_assemble_kernel<M><<<grid_for(P * T, ABLOCK), ABLOCK, sh, st>>>(q, xv, target, P, T, ob, ap, ws);
+    const dim3 grid(grid_for(P, ABLOCK), (unsigned)T);
+    lm_assemble_kernel<M><<<grid, ABLOCK, sh, st>>>(q, xv, target, (int)P, (int)T, ob, ap, ws);
     return CPPFLOW_OK;
 }
 
@@ -550,6 +597,7 @@ static int check_common(int robot, const cppflow_lm_params* params, int64_t P, i
                         size_t workspace_bytes) {
     CPPFLOW_CHECK_ARG(params != nullptr, "params");
     CPPFLOW_CHECK_ARG(P >= 0 && T >= 0, "P, T");
+    CPPFLOW_CHECK_ARG(T <= 65535 && P <= (int64_t)1 << 30, "T must be <= 65535 (grid.y) and P <= 2^30");
     CPPFLOW_CHECK_ARG(d_workspace != nullptr, "workspace");
     CPPFLOW_CHECK_ARG(!params->use_virtual_configs || (params->n_virtual_configs > 0 && 2 * params->n_virtual_configs < T),
                       "2 * n_virtual_configs must be < T (optimization_utils.py:457-459)");
