@@ -347,16 +347,31 @@ __device__ __forceinline__ unsigned self_cull_mask(const float (&mid2)[M::NCAP][
     return mask;
 }
 
-// bit c set <=> capsule c may touch obstacle o
+// number of leading capsules attached to links that no actuated joint moves (capsules are ordered along the chain):
+// their distance to a world-fixed obstacle does not depend on q, so they contribute nothing to the LM normal equations
 template <class M>
+__host__ __device__ constexpr int n_static_capsules() {
+    int first_moving_frame = M::NCHAIN + 1;
+    for (int i = M::NCHAIN - 1; i >= 0; --i)
+        if (M::jtype(i) != J_FIXED) first_moving_frame = i + 1;  // joint i moves frames > i
+    int n = 0;
+    while (n < M::NCAP && M::cap_frame(n) < first_moving_frame) ++n;
+    return n;
+}
+
+static_assert(n_static_capsules<Fetch>() == 1 && n_static_capsules<FetchArm>() == 2 && n_static_capsules<Panda>() == 1,
+              "base link (and the fixed torso of fetch_arm) are the static capsules");
+
+// bit c set <=> capsule c may touch obstacle o; capsules below FIRST are not tested
+template <class M, int FIRST = 0>
 __device__ __forceinline__ unsigned env_cull_mask(const float (&mid2)[M::NCAP][3], const Obstacles& ob, int o) {
     unsigned mask = 0u;
     const float t2[3] = {2.f * ob.t[o][0], 2.f * ob.t[o][1], 2.f * ob.t[o][2]};
     const float lo2[3] = {2.f * ob.lo[o][0], 2.f * ob.lo[o][1], 2.f * ob.lo[o][2]};
     const float hi2[3] = {2.f * ob.hi[o][0], 2.f * ob.hi[o][1], 2.f * ob.hi[o][2]};
     if (ob.has_rot[o]) {
-        static_for<M::NCAP>([&](auto Cc) {
-            constexpr int c = decltype(Cc)::value;
+        static_for<M::NCAP - FIRST>([&](auto Cc) {
+            constexpr int c = decltype(Cc)::value + FIRST;
             constexpr float lim = cap_reach<M>(c);
             constexpr float lim2x4 = 4.f * lim * lim;
             const float v[3] = {mid2[c][0] - t2[0], mid2[c][1] - t2[1], mid2[c][2] - t2[2]};
@@ -372,8 +387,8 @@ __device__ __forceinline__ unsigned env_cull_mask(const float (&mid2)[M::NCAP][3
     } else {
         const float wlo[3] = {lo2[0] + t2[0], lo2[1] + t2[1], lo2[2] + t2[2]};
         const float whi[3] = {hi2[0] + t2[0], hi2[1] + t2[1], hi2[2] + t2[2]};
-        static_for<M::NCAP>([&](auto Cc) {
-            constexpr int c = decltype(Cc)::value;
+        static_for<M::NCAP - FIRST>([&](auto Cc) {
+            constexpr int c = decltype(Cc)::value + FIRST;
             constexpr float lim = cap_reach<M>(c);
             constexpr float lim2x4 = 4.f * lim * lim;
             float dd = 0.f;

@@ -147,13 +147,14 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
     }
     if (prm.use_env) {
         // survivors of up to three obstacles share one 32-bit mask (bit = oo * NCAP + c) so that the lanes of a warp
-        // walk lists of similar length
+        // walk lists of similar length.  Capsules on links that no joint moves have a zero distance gradient: an
+        // active one adds nothing to (A, b), so they are not tested at all.
         constexpr int OGRP = 32 / M::NCAP;
         for (int o0 = 0; o0 < tb.ob.n; o0 += OGRP) {
             unsigned mask = 0u;
 #pragma unroll
             for (int oo = 0; oo < OGRP; ++oo)
-                if (o0 + oo < tb.ob.n) mask |= env_cull_mask<M>(sink.mid2, tb.ob, o0 + oo) << (oo * M::NCAP);
+                if (o0 + oo < tb.ob.n) mask |= env_cull_mask<M, n_static_capsules<M>()>(sink.mid2, tb.ob, o0 + oo) << (oo * M::NCAP);
             while (mask) {
                 const int bit = __ffs(mask) - 1;
                 mask &= mask - 1;

@@ -16,6 +16,28 @@ __device__ __forceinline__ float cfma(const float c, const float x, const float 
     return c == 1.f ? acc + x : (c == -1.f ? acc - x : fmaf(c, x, acc));
 }
 
+// sin and cos of a joint angle: Cody-Waite reduction by pi/2 (two constants: exact to ~1e-15 for |x| < 64, far beyond
+// any joint range) + the cephes single-precision minimax polynomials on [-pi/4, pi/4]; <= 2 ulp, 22 instructions and
+// no slow path (libdevice sincosf carries a Payne-Hanek branch: ~120 SASS instructions per call site, and the FK
+// chain has 7 of them - 14 KB of code in every kernel that walks the chain).
+__device__ __forceinline__ void sincos_joint(float x, float& s, float& c) {
+    const float kf = rintf(x * 0.636619772367581343f);  // x / (pi/2)
+    const int k = __float2int_rn(kf);
+    float r = fmaf(kf, -1.5707963705062866f, x);          // float32(pi/2)
+    r = fmaf(kf, 4.371139000186241e-8f, r);               // pi/2 - float32(pi/2) = -4.371139e-8
+    const float r2 = r * r;
+    float ps = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+    ps = fmaf(ps, r2, -1.6666654611e-1f);
+    ps = fmaf(ps * r2, r, r);                              // sin(r)
+    float pc = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    pc = fmaf(pc, r2, 4.166664568298827e-2f);
+    pc = fmaf(pc * r2, r2, fmaf(-0.5f, r2, 1.f));          // cos(r)
+    const float ss = (k & 1) ? pc : ps;
+    const float cc = (k & 1) ? ps : pc;
+    s = (k & 2) ? -ss : ss;
+    c = ((k + 1) & 2) ? -cc : cc;
+}
+
 struct Frame {
     float R[9];  // row-major world rotation: column k = world direction of the local k axis
     float p[3];
@@ -68,7 +90,7 @@ __device__ __forceinline__ void fk_chain(const float (&q)[M::NDOF], Sink& sink, 
             sink.joint(std::integral_constant<int, d>{}, a, F.p);
             if constexpr (M::jtype(i) == J_REVOLUTE) {
                 float s, c;
-                sincosf(q[d], &s, &c);
+                sincos_joint(q[d], s, c);
                 // columns (u, v) rotate in the plane orthogonal to the axis: u' = c u + s v, v' = -s u + c v
                 constexpr int u = (ax + 1) % 3, v = (ax + 2) % 3;
 #pragma unroll

@@ -21,6 +21,14 @@ def timeit(fn,n=50):
 for name,pm in (('all',all_terms_parameters()),('diff',ALT_LOSS_V2_1_DIFF)):
     prm=ops.make_params(pm)
     print(name,'full step ms (gpu, host-launch): %.3f %.3f'%timeit(lambda: ops.lm_full_step(robot.robot_id,D,prm,x0,None,problem.target_path,P,T,ob,True,out=xo)))
+import ctypes
+lib=_lib.load(); cu,tc,no=ops._obs(ob); st=_lib.stream_ptr(dev)
+for name,pm in (('all',all_terms_parameters()),('diff',ALT_LOSS_V2_1_DIFF)):
+    prm=ops.make_params(pm)
+    ws=ops._workspace(dev, lib.cppflow_lm_full_workspace_bytes(robot.robot_id,P,T), "lm_full")
+    fa=lambda: _lib.check(lib.cppflow_lm_full_assemble(robot.robot_id, prm, _lib.ptr(x0), None, _lib.ptr(problem.target_path), P, T, cu, tc, no, _lib.ptr(ws), ws.numel(), st))
+    fs=lambda: _lib.check(lib.cppflow_lm_full_solve(robot.robot_id, prm, _lib.ptr(x0), P, T, 1, _lib.ptr(ws), ws.numel(), _lib.ptr(xo), st))
+    print(name,'assemble ms: %.3f %.3f'%timeit(fa), ' solve ms: %.3f %.3f'%timeit(fs))
 prm=ops.make_params(ALT_LOSS_V2_1_POSE)
 print('pose step ms: %.3f %.3f'%timeit(lambda: ops.lm_pose_step(robot.robot_id,D,prm,x0,problem.target_path,True,out=xo)))
 print('flags ms: %.3f %.3f'%timeit(lambda: ops.collision_flags(robot.robot_id,D,x0,ob)))
