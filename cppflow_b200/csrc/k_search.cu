@@ -10,6 +10,7 @@
 //   mjac = max_d w;  c = max(mjac, cost[j,t-1]) + ext[i,t];  cost[i,t], memo[i,t] = min_j / first argmin_j.
 #include "common.cuh"
 #include "kinematics.cuh"
+#include <cooperative_groups.h>
 
 namespace cppflow {
 
@@ -166,6 +167,186 @@ dp_sweep_kernel(const float* __restrict__ q, const float* __restrict__ ext, cons
     (void)s_best;
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------
+// Cluster sweep (k <= 512).  The sweep is a chain of T-1 dependent k x k min-max steps: it is bound by the latency of
+// one step, not by throughput.  Eight CTAs of one thread-block cluster split the rows i; a warp owns RPW rows and keeps
+// the mjac values of its rows for the NEXT PF steps in registers (they do not depend on the DP state, so their L2
+// latency is off the critical path).  The (cost, argmin) pair of a finished row is sent to every CTA of the cluster
+// with st.async into distributed shared memory; the store itself signals the destination CTA's mbarrier
+// (complete_tx), so a step needs no cluster barrier and no memory fence: every CTA waits until k pairs have arrived.
+// Two pair buffers, each with its own mbarrier, alternate; a CTA can only start writing buffer b (and signalling its
+// barrier) again after it has received every row of the step in between, i.e. after every warp of the cluster has
+// finished reading b and has seen the previous phase of that barrier complete.  Arithmetic and tie-breaking are those
+// of dp_sweep_kernel (bit-exact with search.py:156-159).
+constexpr int DP_CLUSTER = 8;
+
+__device__ __forceinline__ unsigned dp_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned dp_map_remote(unsigned local_addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+
+template <int RPW, int VPL, int PF, bool MEMO_SMEM>
+__global__ void __cluster_dims__(DP_CLUSTER, 1, 1) __launch_bounds__(1024)
+dp_sweep_cluster_kernel(const float* __restrict__ q, const float* __restrict__ ext, const float* __restrict__ mj, int k,
+                        int T, int D, float* __restrict__ costs, int32_t* __restrict__ memo,
+                        int32_t* __restrict__ chosen, float* __restrict__ best_path) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int rpc = (k + DP_CLUSTER - 1) / DP_CLUSTER;  // rows per CTA
+    extern __shared__ __align__(16) unsigned char dsm[];
+    float2* pairs = reinterpret_cast<float2*>(dsm);                  // [2][k] (cost, argmin bits) of the last two steps
+    float* ext_s = reinterpret_cast<float*>(pairs + 2 * (size_t)k);  // [rpc][T] penalties of this CTA's rows
+    uint16_t* memo_s = reinterpret_cast<uint16_t*>(ext_s + (size_t)rpc * T);  // [T][k] all back-pointers (CTA 0 only)
+    __shared__ __align__(8) uint64_t bar[2];  // bar[t & 1] counts the bytes of step t
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dp_smem_u32(&bar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dp_smem_u32(&bar[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int e = threadIdx.x; e < rpc * T; e += blockDim.x) {
+        const int li = e / T, t = e % T, i = rank * rpc + li;
+        ext_s[e] = i < k ? ext[(int64_t)t * k + i] : 0.f;
+    }
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const float c = ext[i];
+        pairs[i] = make_float2(c, 0.f);
+        if (MEMO_SMEM && rank == 0) memo_s[i] = 0;
+        if (i / rpc == rank) {
+            costs[(int64_t)i * T] = c;
+            memo[(int64_t)i * T] = 0;
+        }
+    }
+    // register ring of mjac values: slot s holds the values of step t + s for this warp's rows
+    float ring[PF + 1][RPW][VPL];
+    auto load_step = [&](int t, float (&dst)[RPW][VPL]) {  // t = index of the step being computed (uses mj[t-1])
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            const int li = warp * RPW + r, i = rank * rpc + li;
+            const bool row_ok = li < rpc && i < k && t < T;
+            const float* row = mj + ((int64_t)(t - 1) * k + i) * k;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int j = lane + 32 * v;
+                dst[r][v] = (row_ok && j < k) ? __ldg(row + j) : INFINITY;
+            }
+        }
+    };
+#pragma unroll
+    for (int s = 0; s <= PF; ++s) load_step(1 + s, ring[s]);
+    // remote addresses of the pair buffers / barrier of CTA `lane` (lanes 0..7 publish)
+    const unsigned peer = lane < DP_CLUSTER ? lane : 0;
+    const unsigned r_pairs = dp_map_remote(dp_smem_u32(pairs), peer);
+    const unsigned r_bar0 = dp_map_remote(dp_smem_u32(&bar[0]), peer);
+    cluster.sync();  // barriers initialised and first buffers filled before the first remote store
+
+    for (int t = 1; t < T; ++t) {
+        const int ph = t - 1;
+        const float2* prev = pairs + (size_t)(ph & 1) * k;
+        const int wr = (ph + 1) & 1;
+        const unsigned my_bar = dp_smem_u32(&bar[t & 1]);
+        const unsigned r_bar = r_bar0 + (unsigned)((t & 1) * sizeof(uint64_t));
+        if (threadIdx.x == 0)  // arm this step's phase: k pairs of 8 bytes will arrive
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(my_bar), "r"(k * 8) : "memory");
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            const int li = warp * RPW + r, i = rank * rpc + li;
+            if (li < rpc && i < k) {
+                const float e = ext_s[li * T + t];
+                float best = INFINITY;
+                int bj = 0x7fffffff;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    const int j = lane + 32 * v;
+                    if (j < k) {
+                        const float val = __fadd_rn(fmaxf(ring[0][r][v], prev[j].x), e);
+                        if (val < best) { best = val; bj = j; }
+                    }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const float ov = __shfl_down_sync(0xffffffffu, best, off);
+                    const int oj = __shfl_down_sync(0xffffffffu, bj, off);
+                    if (ov < best || (ov == best && oj < bj)) { best = ov; bj = oj; }
+                }
+                best = __shfl_sync(0xffffffffu, best, 0);
+                bj = __shfl_sync(0xffffffffu, bj, 0);
+                if (lane < DP_CLUSTER) {  // lane c sends the pair into CTA c and signals its barrier
+                    const unsigned dst = r_pairs + (unsigned)(((size_t)wr * k + i) * sizeof(float2));
+                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
+                                 ::"r"(dst), "r"(__float_as_uint(best)), "r"((unsigned)bj), "r"(r_bar) : "memory");
+                } else if (lane == DP_CLUSTER) {
+                    costs[(int64_t)i * T + t] = best;
+                    memo[(int64_t)i * T + t] = bj;
+                }
+            }
+        }
+        // rotate the register ring and fetch step t + PF + 1
+#pragma unroll
+        for (int s = 0; s < PF; ++s)
+#pragma unroll
+            for (int r = 0; r < RPW; ++r)
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) ring[s][r][v] = ring[s + 1][r][v];
+        load_step(t + PF + 1, ring[PF]);
+        {  // wait until all k pairs of step t have landed in this CTA
+            const unsigned parity = (unsigned)(((t - 1) >> 1) & 1);  // n-th use of bar[t & 1], n = (t - 1) / 2 or t / 2 - 1
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "DPWAIT_%=:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                "@p bra DPDONE_%=;\n"
+                "bra DPWAIT_%=;\n"
+                "DPDONE_%=:\n"
+                "}\n" ::"r"(my_bar), "r"(parity) : "memory");
+        }
+        if (MEMO_SMEM && rank == 0) {
+            const float2* cur = pairs + (size_t)wr * k;
+            for (int i = threadIdx.x; i < k; i += blockDim.x) memo_s[(int64_t)t * k + i] = (uint16_t)__float_as_uint(cur[i].y);
+        }
+    }
+    // final argmin over the last column (first index on ties), then backtrack (search.py:162-173) in CTA 0
+    if (rank == 0) {
+        const float2* last = pairs + (size_t)((T - 1) & 1) * k;
+        __syncthreads();  // memo_s complete
+        if (warp == 0) {
+            float best = INFINITY;
+            int bi = 0x7fffffff;
+            for (int i = lane; i < k; i += 32) {
+                const float v = last[i].x;
+                if (v < best) { best = v; bi = i; }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float ov = __shfl_down_sync(0xffffffffu, best, off);
+                const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+                if (ov < best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (lane == 0) {
+                int i = bi;
+                for (int t = T - 1; t >= 0; --t) {
+                    chosen[t] = i;
+                    i = MEMO_SMEM ? (int)memo_s[(int64_t)t * k + i] : __ldcg(memo + (int64_t)i * T + t);
+                }
+            }
+        }
+        __threadfence_block();
+        __syncthreads();
+        for (int e = threadIdx.x; e < T * D; e += blockDim.x) {
+            const int t = e / D, d = e % D;
+            best_path[e] = q[((int64_t)chosen[t] * T + t) * D + d];
+        }
+    }
+    if (!MEMO_SMEM) __threadfence();  // the other CTAs' memo stores are read by CTA 0's backtrack
+    cluster.sync();  // nobody exits while a peer may still address its shared memory
+}
+
 inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 }  // namespace cppflow
@@ -218,18 +399,44 @@ extern "C" int cppflow_dp_search(int robot, const float* d_q, const uint8_t* d_s
     CPPFLOW_CHECK_LAUNCH();
     const size_t sh_cost = 2 * (size_t)k * sizeof(float);
     const size_t sh_memo = (size_t)T * k * sizeof(uint16_t);
-    const bool memo_smem = sh_cost + sh_memo <= 200 * 1024;
-    const size_t sh = sh_cost + (memo_smem ? sh_memo : 0);
-    const int threads = k >= 512 ? 1024 : (k >= 128 ? 512 : 256);
-    cudaError_t e;
-    if (memo_smem) {
-        e = cudaFuncSetAttribute(dp_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+    cudaError_t e = cudaSuccess;
+    if (k <= 512 && T > 1) {
+        // cluster sweep: 8 CTAs split the rows, mjac prefetched in registers
+        const size_t rpc = (size_t)(k + DP_CLUSTER - 1) / DP_CLUSTER;
+        const size_t sh_base = 2 * sh_cost + rpc * T * sizeof(float);  // two (cost, argmin) pair buffers + penalties
+        const bool memo_smem = sh_base + sh_memo <= 200 * 1024;
+        const size_t sh = sh_base + (memo_smem ? sh_memo : 0);
+        if (sh > 200 * 1024) return fail(CPPFLOW_E_INVALID, "cppflow_dp_search: T = %lld too large for the cluster sweep", (long long)T);
+#define CPPFLOW_DP_LAUNCH(RPW, VPL, PF, MS)                                                                              \
+    do {                                                                                                                 \
+        e = cudaFuncSetAttribute(dp_sweep_cluster_kernel<RPW, VPL, PF, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)sh);                                                                               \
+        if (e == cudaSuccess)                                                                                            \
+            dp_sweep_cluster_kernel<RPW, VPL, PF, MS><<<DP_CLUSTER, 1024, sh, st>>>(d_q, ext, mj, (int)k, (int)T, D,     \
+                                                                                   d_costs, d_memo, d_chosen, d_best_path); \
+    } while (0)
+        if (k <= 256) {
+            if (memo_smem) CPPFLOW_DP_LAUNCH(1, 8, 2, true); else CPPFLOW_DP_LAUNCH(1, 8, 2, false);
+        } else if (k <= 320) {
+            if (memo_smem) CPPFLOW_DP_LAUNCH(2, 10, 1, true); else CPPFLOW_DP_LAUNCH(2, 10, 1, false);
+        } else {
+            if (memo_smem) CPPFLOW_DP_LAUNCH(2, 16, 1, true); else CPPFLOW_DP_LAUNCH(2, 16, 1, false);
+        }
+#undef CPPFLOW_DP_LAUNCH
         if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        dp_sweep_kernel<true><<<1, threads, sh, st>>>(d_q, ext, mj, (int)k, (int)T, D, d_costs, d_memo, d_chosen,
-                                                      d_best_path);
     } else {
-        dp_sweep_kernel<false><<<1, threads, sh, st>>>(d_q, ext, mj, (int)k, (int)T, D, d_costs, d_memo, d_chosen,
-                                                       d_best_path);
+        const bool memo_smem = sh_cost + sh_memo <= 200 * 1024;
+        const size_t sh = sh_cost + (memo_smem ? sh_memo : 0);
+        const int threads = k >= 512 ? 1024 : (k >= 128 ? 512 : 256);
+        if (memo_smem) {
+            e = cudaFuncSetAttribute(dp_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+            if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            dp_sweep_kernel<true><<<1, threads, sh, st>>>(d_q, ext, mj, (int)k, (int)T, D, d_costs, d_memo, d_chosen,
+                                                          d_best_path);
+        } else {
+            dp_sweep_kernel<false><<<1, threads, sh, st>>>(d_q, ext, mj, (int)k, (int)T, D, d_costs, d_memo, d_chosen,
+                                                           d_best_path);
+        }
     }
     CPPFLOW_CHECK_LAUNCH();
     return CPPFLOW_OK;

@@ -133,7 +133,9 @@ def test_dp_search_bit_exact(robots, r, golden):
     assert np.array_equal(best.cpu().numpy(), golden[f"{r}/dp/best_path"])
     assert np.array_equal(joint_limit_almost_violations_3d(rob, q.to(DEV)).cpu().numpy(), golden[f"{r}/dp/jlim"])
     # seeded random case with 2 pi wraps, ties and k not a multiple of 32
-    for (k, T, seed) in [(37, 50, 0), (175, 60, 1), (1, 5, 2), (33, 1, 3)]:
+    # k <= 256 / <= 320 / <= 512 take the three register layouts of the cluster sweep, k > 512 the single-CTA sweep
+    for (k, T, seed) in [(37, 50, 0), (175, 60, 1), (1, 5, 2), (33, 1, 3), (300, 40, 4), (260, 7, 5), (400, 9, 6),
+                         (513, 6, 7), (5, 2, 8), (2, 300, 9)]:
         g = torch.Generator().manual_seed(seed)
         base = random_configs(m, T, seed=seed + 10)
         q = base[None] + 0.4 * torch.randn((k, T, m.ndof), generator=g)
