@@ -1,0 +1,132 @@
+"""GPU parity on the reference's own planning problems (BASELINE.json configs 1-4), through the planner front-end.
+
+For every problem the candidate paths come from the stand-in generator (IKFlow weights are not available offline);
+from there on each stage of `CppFlowPlanner` is compared with the CPU oracle on the SAME candidates:
+  collision flags (bit-exact)  ->  dp_search (memo / costs / path bit-exact)  ->  fixed LM schedule (1e-4 rad),
+and the planner's own alternating loop has to return a path that meets the reference's constraints
+(scripts/evaluate.py:51-56) under the capsule model."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import robots as R, lm as L, search as S
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _problem(name):
+    from cppflow_b200.data_type_utils import problem_from_filename
+
+    return problem_from_filename(None, name, device=DEV)
+
+
+def _cpu_obstacles(problem):
+    cuboids = [c.detach().float().cpu() for c in (problem.obstacles_cuboids or [])]
+    Tcuboids = [t.detach().float().cpu() for t in (problem.obstacles_Tcuboids or [])]
+    return cuboids, Tcuboids
+
+
+def _stage_parity(name, k, schedule="ppdd"):
+    from cppflow_b200 import ops
+    from cppflow_b200.collision_detection import qpaths_batched_env_collisions, qpaths_batched_self_collisions
+    from cppflow_b200.optimization import run_lm_fixed_schedule
+    from cppflow_b200.planners import LmIkCandidateGenerator
+
+    problem = _problem(name)
+    rob = problem.robot
+    m = R.get_model(rob.name)
+    cuboids, Tcuboids = _cpu_obstacles(problem)
+    qs = LmIkCandidateGenerator(seed=3)(problem, k)  # [k, T, D] on the GPU
+    T = problem.n_timesteps
+    assert qs.shape == (k, T, rob.ndof)
+
+    # ---- collision flags: bit-exact outside a 1e-6 m band around zero distance
+    self_v = qpaths_batched_self_collisions(problem, qs)
+    env_v = qpaths_batched_env_collisions(problem, qs)
+    q_cpu = qs.cpu()
+    ref_self = S.qpaths_batched_self_collisions(m, q_cpu)
+    ref_env = S.qpaths_batched_env_collisions(m, q_cpu, cuboids, Tcuboids) if cuboids else torch.zeros_like(ref_self)
+    diff_self = self_v.cpu() != ref_self
+    diff_env = env_v.cpu() != ref_env
+    if diff_self.any() or diff_env.any():  # only configurations with a distance within rounding of zero may differ
+        from oracle import geometry as G
+
+        flat = q_cpu.reshape(k * T, -1).double()
+        near_self = (G.self_collision_distances(m, flat).abs() <= 1e-6).any(dim=1).reshape(k, T)
+        assert not (diff_self & ~near_self).any(), f"{name}: self-collision flags differ away from zero distance"
+        near_env = torch.zeros((k, T), dtype=torch.bool)
+        for cb, Tc in zip(cuboids, Tcuboids):
+            near_env |= (G.env_collision_distances(m, flat, cb.double(), Tc.double()).abs() <= 1e-6).any(dim=1).reshape(k, T)
+        assert not (diff_env & ~near_env).any(), f"{name}: env-collision flags differ away from zero distance"
+
+    # ---- dp_search on the oracle's flags: bit-exact
+    best, memo, costs, chosen = ops.dp_search(rob.robot_id, rob.ndof, qs, ref_self.to(DEV), ref_env.to(DEV))
+    ref_best, ref_memo, ref_costs, ref_chosen = S.dp_search(m, q_cpu, ref_self, ref_env)
+    assert torch.equal(memo.cpu(), ref_memo), name
+    assert torch.equal(costs.cpu(), ref_costs), name
+    assert torch.equal(best.cpu(), ref_best), name
+
+    # ---- fixed LM schedule on the searched path: 1e-4 rad against the fp64 oracle
+    x = run_lm_fixed_schedule(problem, best.contiguous(), schedule).cpu()
+    ref = L.run_fixed_schedule(m, ref_best.double(), problem.target_path.cpu().double(), schedule,
+                               [t.double() for t in Tcuboids], [c.double() for c in cuboids])
+    err = (x.double() - ref).abs().max().item()
+    assert err < 1e-4, (name, err)
+    return problem, best
+
+
+def test_config1_fetch_arm_s_truncated():
+    """BASELINE config 1: tests/fetch_arm__s__truncated.yaml (FetchArm, no obstacles)."""
+    _stage_parity("fetch_arm__s__truncated", k=40)
+
+
+def test_config2_fetch_circle_k175():
+    """BASELINE config 2: fetch__circle, 8-dof Fetch with torso, k = 175 candidates, 4 cuboids."""
+    problem, _ = _stage_parity("fetch__circle", k=175)
+    assert problem.n_timesteps == 295 and len(problem.obstacles_cuboids) == 4
+
+
+def test_config3_panda_1cube():
+    """BASELINE config 3: panda__1cube, capsule-vs-cuboid environment collisions."""
+    problem, _ = _stage_parity("panda__1cube", k=60)
+    assert len(problem.obstacles_cuboids) == 1
+
+
+def test_config4_all_problems_planner_runs():
+    """BASELINE config 4: all 13 benchmark problems through CppFlowPlanner (dp_search + alternating LM loop).  The
+    returned path has the problem's shape, stays inside the joint limits and tracks the target path: the pose
+    constraints of scripts/evaluate.py:51-56 (0.1 mm / 0.1 deg) hold whenever the planner reports a valid plan, and a
+    valid plan is found for most problems.  (The candidates come from the stand-in generator, not IKFlow: from random
+    seeds its LM-IK reaches the target on only ~25 % of the waypoints, and for the Panda problems almost never, so
+    "most" is 9 of 13 at k = 175 today - the bar below leaves two problems of slack.)"""
+    from cppflow_b200.data_type_utils import ALL_PROBLEM_FILENAMES
+    from cppflow_b200.data_types import PlannerSettings
+    from cppflow_b200.planners import CppFlowPlanner, LmIkCandidateGenerator
+
+    n_valid = 0
+    for name in ALL_PROBLEM_FILENAMES:
+        problem = _problem(name)
+        rob = problem.robot
+        planner = CppFlowPlanner(PlannerSettings(k=175, tmax_sec=30.0, anytime_mode_enabled=False, verbosity=0), rob,
+                                 LmIkCandidateGenerator(seed=1))
+        res = planner.generate_plan(problem)
+        q = res.plan.q_path
+        assert q.shape == (problem.n_timesteps, rob.ndof), name
+        assert torch.isfinite(q).all(), name
+        lim = torch.tensor(rob.actuated_joints_limits, device=q.device)
+        assert (q >= lim[:, 0] - 1e-6).all() and (q <= lim[:, 1] + 1e-6).all(), name
+        if res.plan.is_valid:
+            n_valid += 1
+            c = problem.constraints
+            assert res.plan.max_pos_error_cm < c.max_allowed_position_error_cm, name
+            assert res.plan.max_rot_error_deg < c.max_allowed_rotation_error_deg, name
+            assert res.plan.mjac_deg < c.max_allowed_mjac_deg and res.plan.mjac_cm < c.max_allowed_mjac_cm, name
+            # the oracle agrees with the GPU report
+            m = R.get_model(rob.name)
+            cuboids, Tcuboids = _cpu_obstacles(problem)
+            ref = L.path_metrics(m, q.cpu().double(), problem.target_path.cpu().double(),
+                                 [t.double() for t in Tcuboids], [cb.double() for cb in cuboids])
+            assert abs(float(ref["max_pos_cm"]) - res.plan.max_pos_error_cm) < 1e-3, name
+            assert abs(float(ref["max_rot_deg"]) - res.plan.max_rot_error_deg) < 1e-2, name
+    assert n_valid >= 7, f"only {n_valid} valid plans"
