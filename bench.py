@@ -165,6 +165,68 @@ def run_reference(args, rank: int):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# second half of BASELINE.json's metric: plan latency on fetch__circle (config 2): collision flags of k = 175 candidate
+# paths -> dp_search -> run_lm_optimization (the reference's non-anytime call: max 20 steps, return once valid)
+
+
+def plan_latency_gpu(dev, k=175, reps=10):
+    from cppflow_b200.collision_detection import qpaths_batched_collisions
+    from cppflow_b200.data_type_utils import problem_from_filename
+    from cppflow_b200.optimization import run_lm_optimization
+    from cppflow_b200.planners import LmIkCandidateGenerator
+    from cppflow_b200.search import dp_search
+
+    problem = problem_from_filename(None, "fetch__circle", device=dev)
+    qs = LmIkCandidateGenerator(seed=1)(problem, k).contiguous()
+
+    def plan():
+        self_v, env_v = qpaths_batched_collisions(problem, qs)
+        best = dp_search(problem.robot, qs, self_v, env_v, verbosity=0).to(dev)
+        return run_lm_optimization(problem, best, max_n_steps=20, tmax_sec=30.0, return_if_valid_after_n_steps=0,
+                                   convergence_threshold=1e6, verbosity=0)
+
+    for _ in range(2):
+        res = plan()
+    torch.cuda.synchronize(dev)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        res = plan()
+        torch.cuda.synchronize(dev)
+        times.append((time.perf_counter() - t0) * 1e3)
+    return {
+        "problem": "fetch__circle", "k": k, "waypoints": problem.n_timesteps, "unit": "ms",
+        "value": statistics.median(times), "min": min(times), "reps": reps,
+        "lm_steps": res.n_steps_taken + 1, "schedule": res.schedule, "valid": bool(res.is_valid),
+        "what": "host wall clock, candidates resident on the GPU: capsule collision flags -> dp_search -> "
+                "run_lm_optimization(max_n_steps=20, return once valid); one 8-float device->host read per LM step",
+        "candidates": "stand-in LM-IK generator (IKFlow weights unavailable offline), excluded from the timing",
+    }, problem, qs.cpu()
+
+
+def plan_latency_cpu(problem, qs, schedule):
+    """The same plan through the oracle port of the reference's torch path on the host cores (the LM loop replays the
+    step types the GPU run took; the reference's per-step klampt validity check is not included)."""
+    from oracle import robots as OR, lm as OL, search as OS
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = OR.get_model("fetch")
+    cuboids = [c.detach().float().cpu() for c in problem.obstacles_cuboids]
+    Tcuboids = [t.detach().float().cpu() for t in problem.obstacles_Tcuboids]
+    target = problem.target_path.detach().float().cpu()
+    t0 = time.perf_counter()
+    self_v = OS.qpaths_batched_self_collisions(model, qs)
+    env_v = OS.qpaths_batched_env_collisions(model, qs, cuboids, Tcuboids)
+    t1 = time.perf_counter()
+    best = OS.dp_search(model, qs, self_v, env_v)[0]
+    t2 = time.perf_counter()
+    OL.run_fixed_schedule(model, best, target, schedule, Tcuboids, cuboids)
+    t3 = time.perf_counter()
+    return {"value": (t3 - t0) * 1e3, "unit": "ms", "flags_ms": (t1 - t0) * 1e3, "dp_search_ms": (t2 - t1) * 1e3,
+            "lm_ms": (t3 - t2) * 1e3, "schedule": schedule, "cores": os.cpu_count(), "kind": "port"}
+
+
 def workload_config(args, n_gpus):
     return {
         "workload": f"synthetic {args.paths} paths x {args.waypoints} waypoints Fetch 8-DOF, one fused LM iteration "
@@ -375,6 +437,12 @@ def main():
             dist.destroy_process_group()
         return
 
+    plan = None
+    if world == 1:
+        plan, plan_problem, plan_qs = plan_latency_gpu(dev)
+        if not args.no_cpu_baseline:
+            plan["cpu_baseline"] = plan_latency_cpu(plan_problem, plan_qs, plan["schedule"])
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         rate, dt, cores = cpu_reference_step_rate(T, args.cpu_sample_paths, 2, 1)
@@ -409,6 +477,7 @@ def main():
         "roofline_step": roofline_step,
         "kernel_ms": {"lm_assemble_kernel": ms_assemble, "lm_block_solve_kernel": ms_solve},
         "cpu_baseline": cpu_baseline,
+        "plan_latency": plan,
         "argmin": {"cost": best_cost, "rank": best_rank, "path": best_idx},
     }
     print(json.dumps(line))

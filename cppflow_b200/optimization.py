@@ -53,6 +53,7 @@ class OptimizationResult:
     n_steps_taken: int
     is_valid: bool
     parallel_seed_idx: int
+    schedule: str = ""  # not in the reference: the step types taken, 'p' = pose-only, 'd' = differencing
 
 
 def levenberg_marquardt_only_pose(opt_problem: OptimizationProblem, opt_state: OptimizationState,
@@ -141,6 +142,7 @@ def run_lm_alternating_loss(opt_problem: OptimizationProblem, opt_state: Optimiz
     pose_rot_valid = False
     converged = False
     i = 0
+    schedule = ""
     t0 = time()
     for i in range(max_n_steps):
         if pose_pos_valid and pose_rot_valid:
@@ -149,10 +151,12 @@ def run_lm_alternating_loss(opt_problem: OptimizationProblem, opt_state: Optimiz
             printc("  ----> differencing")
             x_new = levenberg_marquardt_full(opt_problem, opt_state, params_diff, clamp=True)
             was_differencing = True
+            schedule += "d"
         else:
             printc("  --> only pose")
             x_new = levenberg_marquardt_only_pose(opt_problem, opt_state, params_pose, clamp=True)
             was_differencing = False
+            schedule += "p"
         opt_state.x = x_new  # clamp_to_joint_limits is fused into both kernels (:259)
 
         metrics = path_metrics(problem, opt_state.x, 1).cpu()  # one sync: TL (:268) and the validity inputs (:318)
@@ -185,7 +189,8 @@ def run_lm_alternating_loss(opt_problem: OptimizationProblem, opt_state: Optimiz
             if i > max_n_steps:
                 break
     x_return = last_valid if last_valid is not None else opt_state.x
-    return OptimizationResult(x_opt=x_return, n_steps_taken=i, is_valid=last_valid is not None, parallel_seed_idx=0)
+    return OptimizationResult(x_opt=x_return, n_steps_taken=i, is_valid=last_valid is not None, parallel_seed_idx=0,
+                              schedule=schedule)
 
 
 def run_lm_optimization(problem: Problem, x_seed: torch.Tensor, tmax_sec: float, max_n_steps: int,
