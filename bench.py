@@ -162,7 +162,7 @@ def run_reference(args, rank: int):
         "e2e": {"value": rate, "unit": "waypoint-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -242,8 +242,21 @@ def workload_config(args, n_gpus):
 # ------------------------------------------------------------------------------------------------------------------
 
 
+def emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else printed to fd 1 (NCCL's version banner, library
+    chatter) was redirected to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -480,7 +493,7 @@ def main():
         "plan_latency": plan,
         "argmin": {"cost": best_cost, "rank": best_rank, "path": best_idx},
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
