@@ -425,7 +425,7 @@ def main():
     }
     solve_bytes = 3 * ws_bytes + 2 * x0.numel() * 4  # read blocks, write (S^-1,u), read them back; read q, write x
     roofline_solve = {
-        "kernel": "lm_block_solve_kernel<Fetch> (block Cholesky sweep, one thread per path)",
+        "kernel": "lm_block_solve_kernel<Fetch> (twisted block-Thomas sweep, two lanes per path, TMA bulk-copy block streaming)",
         "bound": "hbm",
         "achieved": solve_bytes / (ms_solve * 1e-3) / 1e9,
         "peak": hbm_peak,
