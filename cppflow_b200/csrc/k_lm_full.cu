@@ -23,7 +23,10 @@
 
 namespace cppflow {
 
-constexpr int ABLOCK = 128;
+// 256-thread CTAs, two per SM: the 8 warps of a CTA start together and walk the same 68 KB of straight-line code at
+// about the same time, so instruction-cache lines are shared (128-thread CTAs, four per SM: 0.436 ms; 256: 0.409 ms;
+// 512: 0.486 ms - one CTA per SM leaves nothing to cover its ramp-up and drain)
+constexpr int ABLOCK = 256;
 
 template <int D>
 struct BlockLayout {
@@ -75,7 +78,7 @@ __device__ __forceinline__ float wrap_pi_lm(float d) {
 }
 
 template <class M>
-__global__ void __launch_bounds__(ABLOCK, 4)
+__global__ void __launch_bounds__(ABLOCK, 2)
 lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, const float* __restrict__ target,
                    int P, int T, const Obstacles ob, const AssembleParams prm, float* __restrict__ ws) {
     constexpr int D = M::NDOF;
