@@ -155,7 +155,7 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
         constexpr int OGRP = 32 / M::NCAP;
         for (int o0 = 0; o0 < tb.ob.n; o0 += OGRP) {
             unsigned mask = 0u;
-#pragma unroll
+#pragma unroll 1  // one copy of the 9 x 15-instruction cull block (and of its rotated-cuboid variant) in the kernel
             for (int oo = 0; oo < OGRP; ++oo)
                 if (o0 + oo < tb.ob.n) mask |= env_cull_mask<M, n_static_capsules<M>()>(sink.mid2, tb.ob, o0 + oo) << (oo * M::NCAP);
             while (mask) {
