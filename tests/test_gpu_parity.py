@@ -265,6 +265,35 @@ def test_full_step_shapes(robots, P, T):
     assert (out.double() - ref).abs().max() < 1e-4
 
 
+@pytest.mark.parametrize("T", [1, 2, 3, 4])
+def test_full_step_minimal_paths(robots, T):
+    """Shortest paths the twisted sweep can meet (no elimination step at all for T = 1, one side only for T = 2):
+    differencing + collisions without virtual configs (2 * n_virtual_configs < T cannot hold), pose rows on so that
+    the T = 1 system is not singular."""
+    from dataclasses import replace
+
+    from cppflow_b200 import ops
+    from cppflow_b200.lm_hyper_parameters import OptimizationParameters, all_terms_parameters
+
+    r, P = "panda", 19
+    m, target, x0 = synthetic_problem(r, P, T, seed=21)
+    rob = robots[r]
+    cuboids, Tcuboids = cuboid_tensors(OBSTACLES[r])
+    d = dict(all_terms_parameters().__dict__)
+    d.update(use_virtual_configs=False)
+    out = ops.lm_full_step(rob.robot_id, rob.ndof, ops.make_params(OptimizationParameters(**d)), x0.to(DEV), None,
+                           target.to(DEV), P, T, ops.Obstacles(cuboids, Tcuboids), clamp=True).cpu()
+    pms = replace(L.ALL_TERMS, use_virtual_configs=False)
+    ref = L.run_fixed_schedule(m, x0.double(), target.double(), "a", Tcuboids, cuboids, all_pms=pms)
+    ref32 = L.run_fixed_schedule(m, x0, target, "a", Tcuboids, cuboids, all_pms=pms)
+    # same fp32 noise floor as in test_full_step_vs_dense_oracle['all']: J^T J + 1e-6 I has a null-space eigenvalue of
+    # 1e-6 (plus beta for T > 1), so the yardstick is the reference's own fp32 distance from the fp64 result
+    err = (out.double() - ref).abs().reshape(P, T, -1).amax(dim=(1, 2))
+    err32 = (ref32.double() - ref).abs().reshape(P, T, -1).amax(dim=(1, 2))
+    # per path both errors are noise (the ratio scatters over two decades), so the two DISTRIBUTIONS are compared
+    assert err.median() < max(2.5 * err32.median(), 1e-4) and err.max() < max(3.0 * err32.max(), 1e-4), (err, err32)
+
+
 def test_full_step_rejects_bad_arguments(robots):
     from cppflow_b200 import ops, _lib
     from cppflow_b200.lm_hyper_parameters import ALT_LOSS_V2_1_DIFF
