@@ -252,6 +252,7 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
 struct SolveParams {
     float b_rev, b_pri;  // beta of revolute / prismatic dofs
     int do_clamp;
+    unsigned zero;       // always 0; a run-time value so that dependency tokens built from it survive the optimisers
 };
 
 template <int NW>
@@ -285,7 +286,12 @@ __device__ __forceinline__ void store_block(float* __restrict__ p, const float (
 // through a shared staging slot and cp.async.bulk shared -> global.  Warps are independent (no block-level sync).
 constexpr int SOLVE_WARPS = 4;  // a CTA's warp w runs on SM sub-partition w % 4: single-warp CTAs would pile every
                                 // chain of an SM onto one of its four schedulers
-constexpr int SOLVE_RING = 6;   // load slots (steps in flight) per warp
+// Two shared-memory footprints: the deep one (6 load slots + 2 store slots per warp, 209 KB per CTA) owns an SM; the
+// compact one (3 + 1, 105 KB) fits NEXT TO one 256-thread assembly CTA (110 KB, half the register file), so that the
+// solve of one path chunk - a latency-bound chain that keeps 4 warps of an SM busy - runs under the assembly of another
+// chunk (pipeline.ResidentPipeline).  cppflow_lm_full_solve picks by cppflow_lm_params-independent launch flags.
+constexpr int SOLVE_RING_DEEP = 6, SOLVE_STAGES_DEEP = 2;
+constexpr int SOLVE_RING_COMPACT = 3, SOLVE_STAGES_COMPACT = 1;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 template <bool CG = false>
@@ -336,14 +342,14 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // per-warp shared memory: SOLVE_RING load slots + 2 store staging slots, each holding the two blocks of one step
 // (side 1's block is shifted by 64 B so that the LDS.128 / STS.128 of the two sides hit different banks), the q rows of
 // the back-substitution, and one mbarrier per load slot
-template <int D>
+template <int D, int SOLVE_RING, int SOLVE_STAGES>
 struct SolveSmem {
     static constexpr int NV = BlockLayout<D>::NW / 4;                      // float4 per block
     static constexpr int BLK_BYTES = NV * 16 * 16;                         // one block of a 16-path group
     static constexpr int SLOT_BYTES = (2 * BLK_BYTES + 64 + 127) / 128 * 128;
     static constexpr int Q_BYTES = ((D + 3) / 4) * 16 * 32;                // q rows of one step, 32 lanes
     static constexpr int OFF_STAGE = SOLVE_RING * SLOT_BYTES;
-    static constexpr int OFF_Q = OFF_STAGE + 2 * SLOT_BYTES;
+    static constexpr int OFF_Q = OFF_STAGE + SOLVE_STAGES * SLOT_BYTES;
     static constexpr int OFF_BAR = OFF_Q + SOLVE_RING * Q_BYTES;
     static constexpr int BYTES = (OFF_BAR + SOLVE_RING * 8 + 127) / 128 * 128;
     __device__ static unsigned char* part(unsigned char* slot, int side) { return slot + side * (BLK_BYTES + 64); }
@@ -371,7 +377,7 @@ struct BetaSel {
     }
 };
 
-template <class M>
+template <class M, int SOLVE_RING, int SOLVE_STAGES>
 __global__ void __launch_bounds__(32 * SOLVE_WARPS)
 lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const SolveParams prm, float* __restrict__ ws,
                       float* __restrict__ x_out) {
@@ -379,7 +385,7 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
     constexpr int NT = BlockLayout<D>::NT;
     constexpr int NW = BlockLayout<D>::NW;
     constexpr int NV = NW / 4;
-    using SM = SolveSmem<D>;
+    using SM = SolveSmem<D, SOLVE_RING, SOLVE_STAGES>;
     extern __shared__ __align__(128) unsigned char smem_all[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t g = (int64_t)blockIdx.x * SOLVE_WARPS + warp;  // 16-path group of this warp
@@ -406,9 +412,12 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
     __syncwarp();
 
     // lane 0: arm slot (s % RING) and fetch the blocks t0 (side 0) / t1 (side 1); a negative t skips that side
-    auto issue_step = [&](int64_t s, int64_t t0, int64_t t1) {
+    // `token` is the (always zero, but opaque to the compiler) value of slot_read_token below: folding it into the
+    // destination address makes the refill of a slot data-dependent on the completed shared-memory reads of its
+    // previous contents
+    auto issue_step = [&](int64_t s, int64_t t0, int64_t t1, unsigned token = 0u) {
         const int slot = (int)(s % SOLVE_RING);
-        unsigned char* dst = sm + (size_t)slot * SM::SLOT_BYTES;
+        unsigned char* dst = sm + (size_t)slot * SM::SLOT_BYTES + token;
         mbar_expect_tx(bars + slot, (unsigned)SM::BLK_BYTES * ((t0 >= 0) + (t1 >= 0)));
         if (t0 >= 0) bulk_g2s(SM::part(dst, 0), wsg + t0 * SM::BLK_BYTES, SM::BLK_BYTES, bars + slot);
         if (t1 >= 0) bulk_g2s(SM::part(dst, 1), wsg + t1 * SM::BLK_BYTES, SM::BLK_BYTES, bars + slot);
@@ -421,6 +430,20 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
             const float4 f = *SM::blk(part, k, l);
             v[4 * k] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w;
         }
+    };
+    // WAR hazard between the generic-proxy reads of a ring slot (LDS) and the async-proxy refill of the same slot
+    // (TMA): an LDS only has to be ISSUED before the instructions after it run, and __syncwarp() of a converged warp is
+    // no instruction at all, so nothing orders the UBLKCP of lane 0 after the reads.  Measured: with two solve CTAs per
+    // SM the refill regularly landed first and the back-substitution used rows of the block three steps ahead.
+    // The token consumes one register of every LDS.128 of every lane (the warp-wide OR cannot complete before every
+    // lane's loads have returned) and is folded into the refill's address.
+    auto slot_read_token = [&](const float (&v)[NW], bool valid) -> unsigned {
+        unsigned acc = 0u;
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) acc |= __float_as_uint(v[4 * k]);
+        }
+        return __reduce_or_sync(0xffffffffu, acc & prm.zero);  // prm.zero = 0 at run time: neither nvcc nor ptxas can fold it
     };
     auto store_x = [&](int64_t t, float (&xn)[D]) {
         if (prm.do_clamp) {
@@ -456,11 +479,11 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
         float blk[NW];
         wait_step(k);
         if (mine) read_block(k, blk);
-        __syncwarp();  // every lane has read the slot: it can be refilled
+        const unsigned token = slot_read_token(blk, mine);  // every lane's reads of the slot have returned: refill it
         if (lane == 0) {
             const int64_t j = k + SOLVE_RING;
-            if (j < n_iter) issue_step(j, j < n0 ? j : -1, j < n1 ? T - 1 - j : -1);
-            bulk_wait_read<1>();  // the staging slot used two steps ago has been read out
+            if (j < n_iter) issue_step(j, j < n0 ? j : -1, j < n1 ? T - 1 - j : -1, token);
+            bulk_wait_read<SOLVE_STAGES - 1>();  // the staging slot about to be reused has been read out
         }
         if (mine) {
             static_for<D>([&](auto Ii) {
@@ -474,7 +497,7 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
             sweep_neg_inverse<D>(nS, u);
         }
         __syncwarp();  // lane 0's bulk_wait_read is done
-        unsigned char* stage = sm + SM::OFF_STAGE + (size_t)(k & 1) * SM::SLOT_BYTES;
+        unsigned char* stage = sm + SM::OFF_STAGE + (size_t)(k % SOLVE_STAGES) * SM::SLOT_BYTES;
         if (mine) {  // block t <- (-S_t^-1 packed, u_t)
             float v[NW];
 #pragma unroll
@@ -563,10 +586,11 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
 #pragma unroll
             for (int d = 0; d < D; ++d) xn[d] = *SM::qv(sm, qslot, d, lane);
         }
-        __syncwarp();
+        const unsigned token = slot_read_token(blk, mine);
         if (lane == 0) {
             const int64_t rn = r + SOLVE_RING;
-            if (rn < n_iter) issue_step(n_iter + rn, n0 - 1 - rn >= 0 ? n0 - 1 - rn : -1, n1 - 1 - rn >= 0 ? T - 1 - (n1 - 1 - rn) : -1);
+            if (rn < n_iter)
+                issue_step(n_iter + rn, n0 - 1 - rn >= 0 ? n0 - 1 - rn : -1, n1 - 1 - rn >= 0 ? T - 1 - (n1 - 1 - rn) : -1, token);
         }
         if (mine) {
             const int64_t kn = k - SOLVE_RING;
@@ -619,7 +643,7 @@ static void make_params(const cppflow_lm_params* p, int n_obstacles, int do_clam
     ap.n_virtual = p->n_virtual_configs;
     ap.use_self = p->use_self_collisions;
     ap.use_env = p->use_env_collisions && n_obstacles > 0;
-    sp.do_clamp = do_clamp;
+    sp.do_clamp = do_clamp ? 1 : 0;
 }
 
 template <class M>
@@ -640,22 +664,45 @@ static int launch_assemble(const cppflow_lm_params* p, const float* q, const flo
     return CPPFLOW_OK;
 }
 
+template <class M, int RING, int STAGES>
+static int launch_solve_variant(const SolveParams& sp, const float* q, int64_t P, int64_t T, bool high_priority,
+                                float* ws, float* x_out, cudaStream_t st) {
+    const size_t sh = SolveSmem<M::NDOF, RING, STAGES>::BYTES * SOLVE_WARPS;
+    auto kern = lm_block_solve_kernel<M, RING, STAGES>;
+    static bool attr_set = false;  // per template instantiation
+    static int prio_high = 0;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+        if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        prio_high = greatest;
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid_for(P, 16 * SOLVE_WARPS));
+    cfg.blockDim = dim3(32 * SOLVE_WARPS);
+    cfg.dynamicSmemBytes = sh;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributePriority;  // CTAs of this launch are dispatched before pending CTAs of assembly
+    at[0].val.priority = prio_high;          // launches on other streams (the block scheduler is otherwise FIFO)
+    cfg.attrs = at;
+    cfg.numAttrs = high_priority ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, q, P, T, sp, ws, x_out);
+    if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "lm_block_solve launch: %s", cudaGetErrorString(e));
+    return CPPFLOW_OK;
+}
+
 template <class M>
-static int launch_solve(const cppflow_lm_params* p, const float* q, int64_t P, int64_t T, int do_clamp, float* ws,
+static int launch_solve(const cppflow_lm_params* p, const float* q, int64_t P, int64_t T, int flags, float* ws,
                         float* x_out, cudaStream_t st) {
     AssembleParams ap;
     SolveParams sp;
-    make_params<M>(p, 0, do_clamp, ap, sp);
-    const size_t sh = SolveSmem<M::NDOF>::BYTES * SOLVE_WARPS;
-    static bool attr_set = false;  // per template instantiation
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(lm_block_solve_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
-        if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set = true;
-    }
-    const unsigned grid = grid_for(P, 16 * SOLVE_WARPS);
-    lm_block_solve_kernel<M><<<grid, 32 * SOLVE_WARPS, sh, st>>>(q, P, T, sp, ws, x_out);
-    return CPPFLOW_OK;
+    make_params<M>(p, 0, flags & CPPFLOW_LM_CLAMP, ap, sp);
+    if (flags & CPPFLOW_LM_OVERLAP)
+        return launch_solve_variant<M, SOLVE_RING_COMPACT, SOLVE_STAGES_COMPACT>(sp, q, P, T, true, ws, x_out, st);
+    return launch_solve_variant<M, SOLVE_RING_DEEP, SOLVE_STAGES_DEEP>(sp, q, P, T, false, ws, x_out, st);
 }
 
 template <class M>

@@ -8,6 +8,7 @@ from . import _lib
 from ._lib import LmParamsC, ptr, stream_ptr, require_cuda, check
 
 ROBOT_IDS = {"fetch": 0, "fetch_arm": 1, "panda": 2}
+LM_CLAMP, LM_OVERLAP = 1, 2  # CPPFLOW_LM_CLAMP / CPPFLOW_LM_OVERLAP (include/cppflow_b200.h)
 
 
 def _info(robot_id: int) -> _lib.RobotInfoC:
@@ -185,7 +186,11 @@ def _workspace(device, nbytes: int, key: str) -> torch.Tensor:
 
 def lm_full_step(rid: int, ndof: int, params: LmParamsC, q: torch.Tensor, xv: Optional[torch.Tensor],
                  target: Optional[torch.Tensor], P: int, T: int, ob: Optional[Obstacles], clamp: bool,
-                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 out: Optional[torch.Tensor] = None, overlap: bool = False,
+                 workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """levenberg_marquardt_full (+ clamp) for P paths of T waypoints on the current stream.  `overlap`: launch the
+    solve with CPPFLOW_LM_OVERLAP (compact footprint, high launch priority) - for callers that run several chunks
+    of paths on several streams (pipeline.ResidentPipeline), which must also pass one `workspace` per stream."""
     q = _check_q(q, ndof)
     assert q.shape[0] == P * T, f"x must have P*T = {P * T} rows, has {q.shape[0]}"
     if xv is not None:
@@ -196,10 +201,15 @@ def lm_full_step(rid: int, ndof: int, params: LmParamsC, q: torch.Tensor, xv: Op
         assert target.shape == (T, 7), f"target_path must be [{T}, 7], is {tuple(target.shape)}"
     lib = _lib.load()
     nbytes = lib.cppflow_lm_full_workspace_bytes(rid, P, T)
-    ws = _workspace(q.device, nbytes, "lm_full")
+    if workspace is None:
+        ws = _workspace(q.device, nbytes, "lm_full")
+    else:
+        ws = workspace
+        assert ws.is_cuda and ws.dtype == torch.uint8 and ws.numel() >= nbytes, "workspace too small"
     x_out = torch.empty_like(q) if out is None else out
     cu, tc, no = _obs(ob)
-    check(lib.cppflow_lm_full_step(rid, params, ptr(q), ptr(xv), ptr(target), P, T, cu, tc, no, int(clamp), ptr(ws),
+    flags = (LM_CLAMP if clamp else 0) | (LM_OVERLAP if overlap else 0)
+    check(lib.cppflow_lm_full_step(rid, params, ptr(q), ptr(xv), ptr(target), P, T, cu, tc, no, flags, ptr(ws),
                                    ws.numel(), ptr(x_out), stream_ptr(q.device)))
     return x_out
 

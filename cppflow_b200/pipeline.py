@@ -96,3 +96,74 @@ class HostPipeline:
         for s in [self.s_out, self.s_in] + self.s_run:
             cur.wait_stream(s)
         return out_host
+
+
+class ResidentPipeline:
+    """LM iterations over device-resident paths with the two kernels of the step overlapped across path chunks.
+
+    One iteration is assembly (FP32-bound, fills every SM) followed by the block solve (a latency-bound chain: 4 warps
+    per 64 paths, each busy for the whole 0.25 ms however few paths there are).  Back to back they add up.  Paths are
+    independent, so the path set is cut into `n_chunks` chunks, each with its own stream and workspace, and the
+    iterations of a chunk are enqueued on its stream without any cross-chunk join: while chunk A is in its solve, chunk
+    B is in the assembly of the same or the next iteration.  For that to happen on the SMs the solve is launched with
+    CPPFLOW_LM_OVERLAP: a 105 KB shared-memory footprint that fits next to one 256-thread assembly CTA, and the highest
+    launch priority so that its CTAs are dispatched before the thousands of pending assembly CTAs of the other chunks.
+    Chunks are multiples of 256 paths (the assembly CTA) where P allows."""
+
+    def __init__(self, problem: Problem, n_paths: int, params: Optional[OptimizationParameters] = None,
+                 n_chunks: int = 4, device=None, overlap: bool = True):
+        self.problem = problem
+        self.robot = problem.robot
+        self.T = problem.n_timesteps
+        self.P = n_paths
+        self.device = problem.target_path.device if device is None else torch.device(device)
+        self.prm = ops.make_params(params if params is not None else all_terms_parameters())
+        self.overlap = overlap
+        gran = 256 if n_paths >= 256 * n_chunks else 16 if n_paths >= 16 * n_chunks else 1
+        units = (n_paths + gran - 1) // gran
+        n_chunks = max(1, min(n_chunks, units))
+        base, rem = divmod(units, n_chunks)
+        self.chunks = []
+        start = 0
+        for c in range(n_chunks):
+            n = min((base + (1 if c < rem else 0)) * gran, n_paths - start)
+            if n > 0:
+                self.chunks.append((start, n))
+            start += n
+        self.streams = [torch.cuda.Stream(self.device) for _ in self.chunks]
+        lib = ops._lib.load()
+        self.ws = [torch.empty((lib.cppflow_lm_full_workspace_bytes(self.robot.robot_id, n, self.T),), device=self.device,
+                               dtype=torch.uint8) for _, n in self.chunks]
+
+    def begin(self):
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            s.wait_stream(cur)
+
+    def end(self):
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            cur.wait_stream(s)
+
+    def enqueue_step(self, x: torch.Tensor, out: torch.Tensor, clamp: bool = True):
+        """One LM iteration x -> out ([P*T, D] device tensors) for every chunk, each on its own stream; call between
+        begin() and end().  Steps enqueued back to back pipeline across chunks."""
+        T, D, rid = self.T, self.robot.ndof, self.robot.robot_id
+        for (p0, n), s, ws in zip(self.chunks, self.streams, self.ws):
+            sl = slice(p0 * T, (p0 + n) * T)
+            with torch.cuda.stream(s):
+                ops.lm_full_step(rid, D, self.prm, x[sl], None, self.problem.target_path, n, T,
+                                 self.problem.obstacle_tables, clamp, out=out[sl], overlap=self.overlap, workspace=ws)
+
+    def iterate(self, x: torch.Tensor, n_iters: int, clamp: bool = True) -> torch.Tensor:
+        """n_iters dependent LM iterations (x <- step(x)); returns the refined paths (a new tensor; x is kept)."""
+        assert x.is_cuda and x.shape == (self.P * self.T, self.robot.ndof)
+        bufs = [torch.empty_like(x), torch.empty_like(x)]
+        src = x
+        self.begin()
+        for i in range(n_iters):
+            dst = bufs[i % 2]
+            self.enqueue_step(src, dst, clamp)
+            src = dst
+        self.end()
+        return src if n_iters > 0 else x.clone()

@@ -140,6 +140,13 @@ int cppflow_lm_full_assemble(int robot, const cppflow_lm_params* params, const f
 int cppflow_lm_full_solve(int robot, const cppflow_lm_params* params, const float* d_q, int64_t P, int64_t T,
                           int do_clamp, void* d_workspace, size_t workspace_bytes, float* d_x_out, void* stream);
 
+/* `do_clamp` of cppflow_lm_full_step / cppflow_lm_full_solve is a bit set: CPPFLOW_LM_CLAMP (= 1, the reference's
+ * clamp_to_joint_limits after the step) | CPPFLOW_LM_OVERLAP: the solve is launched with the compact shared-memory
+ * footprint (fits on an SM next to one assembly CTA) and the highest launch priority, so that it runs UNDER the
+ * assembly of another chunk of paths enqueued on another stream (same results bit for bit). */
+#define CPPFLOW_LM_CLAMP 1
+#define CPPFLOW_LM_OVERLAP 2
+
 /* joint_limit_almost_violations_3d(robot, qs, eps_revolute, eps_prismatic) -> float32 0/1 [n]  (search.py:25-52) */
 int cppflow_joint_limit_flags(int robot, const float* d_q, int64_t n, float eps_revolute, float eps_prismatic,
                               float* d_flags, void* stream);

@@ -305,3 +305,47 @@ def test_full_step_rejects_bad_arguments(robots):
                          None, clamp=True)
     with pytest.raises(RuntimeError):  # CPU tensors are refused: there is no CPU fallback
         ops.forward_kinematics(rob.robot_id, rob.ndof, x0)
+
+
+def test_full_step_full_size_path_independence(robots):
+    """BASELINE.json's full size (8192 paths x 300 waypoints, every term on).  Paths are independent, so the result of a
+    path must not depend on how many other paths are in the launch, which solve footprint is used (deep: one CTA per SM;
+    CPPFLOW_LM_OVERLAP: compact, several CTAs per SM) or how the path set is chunked over streams: all bit-identical.
+    This is the regression test of a shared-memory WAR hazard (TMA refill of a ring slot against the LDS reads of its
+    previous contents) that only showed with two solve CTAs on one SM, i.e. never at the sizes the oracle can check."""
+    from cppflow_b200 import ops
+    from cppflow_b200.lm_hyper_parameters import all_terms_parameters
+    from cppflow_b200.pipeline import ResidentPipeline
+    from cppflow_b200.synthetic import synthetic_problem as gpu_problem, synthetic_seeds_host
+
+    rob = robots["fetch"]
+    P, T, D = 8192, 300, rob.ndof
+    problem = gpu_problem(rob, T, device=DEV)
+    _, xh = synthetic_seeds_host(rob, P, T)
+    x0 = xh.to(DEV)
+    prm = ops.make_params(all_terms_parameters())
+    ob = problem.obstacle_tables
+
+    def step(x, n_paths, **kw):
+        return ops.lm_full_step(rob.robot_id, D, prm, x, None, problem.target_path, n_paths, T, ob, True, **kw)
+
+    ref = step(x0, P)
+    for _ in range(3):  # the hazard was timing dependent: ~25 % of the paths were hit in every launch
+        assert torch.equal(step(x0, P), ref)
+        assert torch.equal(step(x0, P, overlap=True), ref)
+    for g in (0, 7, 255, 511):  # 16-path groups on their own
+        sl = slice(g * 16 * T, (g + 1) * 16 * T)
+        assert torch.equal(step(x0[sl].contiguous(), 16), ref[sl])
+    sl = slice(5 * T, 6 * T)  # a single path
+    assert torch.equal(step(x0[sl].contiguous(), 1), ref[sl])
+
+    seq = x0
+    for _ in range(3):
+        seq = step(seq, P)
+    for n_chunks in (1, 3, 4):
+        pipe = ResidentPipeline(problem, P, all_terms_parameters(), n_chunks=n_chunks)
+        assert torch.equal(pipe.iterate(x0, 3), seq), n_chunks
+    # and the full-size result is a descent step: every path's pose error shrinks
+    m0 = ops.path_metrics(rob.robot_id, D, x0, problem.target_path, P, T, ob)
+    m1 = ops.path_metrics(rob.robot_id, D, seq, problem.target_path, P, T, ob)
+    assert (m1[:, 0] < m0[:, 0]).all() and float(m1[:, 0].max()) < 0.5 * float(m0[:, 0].max())
