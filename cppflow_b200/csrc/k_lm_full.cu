@@ -16,7 +16,7 @@
 // Kernel A (assembly) evaluates FK, the Jacobian, all capsule distances and the active gradients of one waypoint per
 // thread and writes the packed (A_tt, b_t) block (44 floats for D = 8) to the workspace.
 // Kernel B (solve) runs a twisted block-Thomas elimination per path (two lanes per path, one from each end), streaming
-// the blocks with TMA bulk copies, and writes clamp(x + dx).  Nothing of size (T*D)^2 is ever formed.
+// the blocks in with TMA bulk copies, and writes clamp(x + dx).  Nothing of size (T*D)^2 is ever formed.
 #include "common.cuh"
 #include "collision.cuh"
 #include "linalg.cuh"
@@ -283,15 +283,17 @@ __device__ __forceinline__ void store_block(float* __restrict__ p, const float (
 // (-S^-1, u), read them back).  A warp owns one 16-path group, whose blocks are 2816 contiguous bytes per waypoint
 // (BlockLayout), and moves them with TMA bulk copies: one elected lane arms an mbarrier and issues
 // cp.async.bulk global -> shared for the two blocks (one per side) of a step, SOLVE_RING steps ahead; results go back
-// through a shared staging slot and cp.async.bulk shared -> global.  Warps are independent (no block-level sync).
-constexpr int SOLVE_WARPS = 4;  // a CTA's warp w runs on SM sub-partition w % 4: single-warp CTAs would pile every
-                                // chain of an SM onto one of its four schedulers
-// Two shared-memory footprints: the deep one (6 load slots + 2 store slots per warp, 209 KB per CTA) owns an SM; the
-// compact one (3 + 1, 105 KB) fits NEXT TO one 256-thread assembly CTA (110 KB, half the register file), so that the
-// solve of one path chunk - a latency-bound chain that keeps 4 warps of an SM busy - runs under the assembly of another
-// chunk (pipeline.ResidentPipeline).  cppflow_lm_full_solve picks by cppflow_lm_params-independent launch flags.
-constexpr int SOLVE_RING_DEEP = 6, SOLVE_STAGES_DEEP = 2;
-constexpr int SOLVE_RING_COMPACT = 3, SOLVE_STAGES_COMPACT = 1;
+// with coalesced 16-byte stores straight from registers.  Warps are independent (no block-level sync).
+constexpr int SOLVE_WARPS_DEFAULT = 4;  // a CTA's warp w runs on SM sub-partition w % 4: single-warp CTAs would pile
+                                        // every chain of an SM onto one of its four schedulers
+// Two ring depths: 3 slots per warp (80 KB per CTA, two CTAs per SM) is the fastest on its own; 4 slots (109 KB) is
+// the deepest that still fits NEXT TO one 256-thread assembly CTA (110 KB, half the register file) and is used with
+// CPPFLOW_LM_OVERLAP, where the solve of one path chunk - a latency-bound chain that keeps 4 warps of an SM busy - runs
+// under the assembly of another chunk (pipeline.ResidentPipeline) and shares the SM's issue slots with it.
+// Measured at P = 8192, T = 300 (single stream / 4 chunks overlapped, ms per iteration): ring 2: 0.665 / 0.639,
+// ring 3: 0.646 / 0.568, ring 4: 0.657 / 0.560, ring 6 (one CTA per SM): 0.660 / 0.618.
+constexpr int SOLVE_RING_ALONE = 3;
+constexpr int SOLVE_RING_OVERLAP = 4;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 template <bool CG = false>
@@ -328,28 +330,16 @@ __device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned 
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-// TMA bulk copy shared -> global, tracked by the issuing thread's bulk async-group
-__device__ __forceinline__ void bulk_s2g(void* gmem, const void* smem, unsigned bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem), "r"(smem_u32(smem)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// per-warp shared memory: SOLVE_RING load slots + 2 store staging slots, each holding the two blocks of one step
-// (side 1's block is shifted by 64 B so that the LDS.128 / STS.128 of the two sides hit different banks), the q rows of
+// per-warp shared memory: SOLVE_RING load slots, each holding the two blocks of one step
+// (side 1's block is shifted by 64 B so that the LDS.128 of the two sides hit different banks), the q rows of
 // the back-substitution, and one mbarrier per load slot
-template <int D, int SOLVE_RING, int SOLVE_STAGES>
+template <int D, int SOLVE_RING>
 struct SolveSmem {
     static constexpr int NV = BlockLayout<D>::NW / 4;                      // float4 per block
     static constexpr int BLK_BYTES = NV * 16 * 16;                         // one block of a 16-path group
     static constexpr int SLOT_BYTES = (2 * BLK_BYTES + 64 + 127) / 128 * 128;
     static constexpr int Q_BYTES = ((D + 3) / 4) * 16 * 32;                // q rows of one step, 32 lanes
-    static constexpr int OFF_STAGE = SOLVE_RING * SLOT_BYTES;
-    static constexpr int OFF_Q = OFF_STAGE + SOLVE_STAGES * SLOT_BYTES;
+    static constexpr int OFF_Q = SOLVE_RING * SLOT_BYTES;
     static constexpr int OFF_BAR = OFF_Q + SOLVE_RING * Q_BYTES;
     static constexpr int BYTES = (OFF_BAR + SOLVE_RING * 8 + 127) / 128 * 128;
     __device__ static unsigned char* part(unsigned char* slot, int side) { return slot + side * (BLK_BYTES + 64); }
@@ -377,15 +367,15 @@ struct BetaSel {
     }
 };
 
-template <class M, int SOLVE_RING, int SOLVE_STAGES>
-__global__ void __launch_bounds__(32 * SOLVE_WARPS)
+template <class M, int SOLVE_RING, int SOLVE_WARPS>
+__global__ void __launch_bounds__(32 * SOLVE_WARPS, 512 / (32 * SOLVE_WARPS))
 lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const SolveParams prm, float* __restrict__ ws,
                       float* __restrict__ x_out) {
     constexpr int D = M::NDOF;
     constexpr int NT = BlockLayout<D>::NT;
     constexpr int NW = BlockLayout<D>::NW;
     constexpr int NV = NW / 4;
-    using SM = SolveSmem<D, SOLVE_RING, SOLVE_STAGES>;
+    using SM = SolveSmem<D, SOLVE_RING>;
     extern __shared__ __align__(128) unsigned char smem_all[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t g = (int64_t)blockIdx.x * SOLVE_WARPS + warp;  // 16-path group of this warp
@@ -483,7 +473,6 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
         if (lane == 0) {
             const int64_t j = k + SOLVE_RING;
             if (j < n_iter) issue_step(j, j < n0 ? j : -1, j < n1 ? T - 1 - j : -1, token);
-            bulk_wait_read<SOLVE_STAGES - 1>();  // the staging slot about to be reused has been read out
         }
         if (mine) {
             static_for<D>([&](auto Ii) {
@@ -496,9 +485,12 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
             });
             sweep_neg_inverse<D>(nS, u);
         }
-        __syncwarp();  // lane 0's bulk_wait_read is done
-        unsigned char* stage = sm + SM::OFF_STAGE + (size_t)(k % SOLVE_STAGES) * SM::SLOT_BYTES;
-        if (mine) {  // block t <- (-S_t^-1 packed, u_t)
+        // block t <- (-S_t^-1 packed, u_t) with 16-byte generic stores: a warp instruction covers 256 contiguous bytes
+        // per side.  (An earlier version staged the block in shared memory and sent it with a TMA bulk store: the
+        // staging, fence.proxy.async and bulk-group bookkeeping cost ~500 cycles per step, 0.29 -> 0.24 ms without.)
+        // The TMA loads of the back-substitution read these blocks through the async proxy: the fences after the loop
+        // make them visible.
+        if (mine) {
             float v[NW];
 #pragma unroll
             for (int i = 0; i < NT; ++i) v[i] = nS[i];
@@ -506,18 +498,14 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
             for (int d = 0; d < D; ++d) v[NT + d] = u[d];
 #pragma unroll
             for (int i = NT + D; i < NW; ++i) v[i] = 0.f;
-            unsigned char* part = SM::part(stage, side);
+            float4* dstg = reinterpret_cast<float4*>(wsg + (side == 0 ? k : T - 1 - k) * SM::BLK_BYTES) + l;
 #pragma unroll
-            for (int i = 0; i < NV; ++i) *SM::blk(part, i, l) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
-        fence_proxy_async();  // generic-proxy writes -> visible to the bulk (async-proxy) store
-        __syncwarp();
-        if (lane == 0) {
-            if (k < n0) bulk_s2g(wsg + k * SM::BLK_BYTES, SM::part(stage, 0), SM::BLK_BYTES);
-            if (k < n1) bulk_s2g(wsg + (T - 1 - k) * SM::BLK_BYTES, SM::part(stage, 1), SM::BLK_BYTES);
-            bulk_commit();
+            for (int i = 0; i < NV; ++i) dstg[i * 16] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
     }
+    __threadfence();                                  // the generic stores above are performed ...
+    asm volatile("fence.proxy.async;" ::: "memory");  // ... and ordered before the async-proxy (TMA) reads below
+    __syncwarp();
 
     // ---- back-substitution loads (steps s = n_iter .. 2 n_iter - 1, block order k = n_side-1 ... 0) start while the
     // middle block is factorised; they read what the bulk stores above wrote, so those have to be complete
@@ -532,7 +520,6 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
     };
     auto t_of = [&](int64_t k) { return side == 0 ? k : T - 1 - k; };
     if (lane == 0) {
-        bulk_wait<0>();
         for (int64_t r = 0; r < SOLVE_RING && r < n_iter; ++r)
             issue_step(n_iter + r, n0 - 1 - r >= 0 ? n0 - 1 - r : -1, n1 - 1 - r >= 0 ? T - 1 - (n1 - 1 - r) : -1);
     }
@@ -664,11 +651,11 @@ static int launch_assemble(const cppflow_lm_params* p, const float* q, const flo
     return CPPFLOW_OK;
 }
 
-template <class M, int RING, int STAGES>
+template <class M, int RING, int WARPS = SOLVE_WARPS_DEFAULT>
 static int launch_solve_variant(const SolveParams& sp, const float* q, int64_t P, int64_t T, bool high_priority,
                                 float* ws, float* x_out, cudaStream_t st) {
-    const size_t sh = SolveSmem<M::NDOF, RING, STAGES>::BYTES * SOLVE_WARPS;
-    auto kern = lm_block_solve_kernel<M, RING, STAGES>;
+    const size_t sh = SolveSmem<M::NDOF, RING>::BYTES * WARPS;
+    auto kern = lm_block_solve_kernel<M, RING, WARPS>;
     static bool attr_set = false;  // per template instantiation
     static int prio_high = 0;
     if (!attr_set) {
@@ -680,8 +667,8 @@ static int launch_solve_variant(const SolveParams& sp, const float* q, int64_t P
         attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid_for(P, 16 * SOLVE_WARPS));
-    cfg.blockDim = dim3(32 * SOLVE_WARPS);
+    cfg.gridDim = dim3(grid_for(P, 16 * WARPS));
+    cfg.blockDim = dim3(32 * WARPS);
     cfg.dynamicSmemBytes = sh;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -700,9 +687,8 @@ static int launch_solve(const cppflow_lm_params* p, const float* q, int64_t P, i
     AssembleParams ap;
     SolveParams sp;
     make_params<M>(p, 0, flags & CPPFLOW_LM_CLAMP, ap, sp);
-    if (flags & CPPFLOW_LM_OVERLAP)
-        return launch_solve_variant<M, SOLVE_RING_COMPACT, SOLVE_STAGES_COMPACT>(sp, q, P, T, true, ws, x_out, st);
-    return launch_solve_variant<M, SOLVE_RING_DEEP, SOLVE_STAGES_DEEP>(sp, q, P, T, false, ws, x_out, st);
+    if (flags & CPPFLOW_LM_OVERLAP) return launch_solve_variant<M, SOLVE_RING_OVERLAP>(sp, q, P, T, true, ws, x_out, st);
+    return launch_solve_variant<M, SOLVE_RING_ALONE>(sp, q, P, T, false, ws, x_out, st);
 }
 
 template <class M>
