@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--paths", type=int, default=8192)
     ap.add_argument("--waypoints", type=int, default=300)
+    ap.add_argument("--chunks", type=int, default=4, help="path chunks (streams) of the pipelined LM iterations")
     ap.add_argument("--cpu-sample-paths", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -234,7 +235,10 @@ def workload_config(args, n_gpus):
         "paths_per_gpu": args.paths,
         "waypoints": args.waypoints,
         "robot": "fetch",
-        "parallelism": f"paths sharded over {n_gpus} GPU(s), no data-path collective",
+        "parallelism": f"paths sharded over {n_gpus} GPU(s), no data-path collective; per GPU the K iterations run as "
+                       f"{args.chunks} independent path chunks on {args.chunks} streams (solve of one chunk under the assembly "
+                       "of another), every chunk doing all K iterations",
+        "chunks_per_gpu": args.chunks,
         "l2": "no flush: each step streams ~1.9 GB (q, x_new, 433 MB block workspace written+read twice) >> 126 MB L2",
     }
 
@@ -297,6 +301,12 @@ def main():
     def step(src=x0, dst=x_out):
         return ops.lm_full_step(rid, D, prm, src, None, problem.target_path, P, T, ob, True, out=dst)
 
+    # the K timed iterations run chunk-pipelined: the path set is cut into `--chunks` chunks with one stream each, and
+    # the block solve of one chunk runs under the assembly of another (pipeline.ResidentPipeline, CPPFLOW_LM_OVERLAP)
+    from cppflow_b200.pipeline import ResidentPipeline
+
+    rpipe = ResidentPipeline(problem, P, all_terms_parameters(), n_chunks=args.chunks)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -304,6 +314,10 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         step()
+    rpipe.begin()
+    for _ in range(max(args.warmup, 3)):
+        rpipe.enqueue_step(x0, x_out)
+    rpipe.end()
     # warm up the once-per-job tail too (path metrics kernel, NCCL gather, torch argmin): first calls load modules
     gather_costs_and_argmin(ops.path_metrics(rid, D, x_out, problem.target_path, P, T, ob), problem.constraints, rank, world)
     barrier()
@@ -315,11 +329,13 @@ def main():
     barrier()
     e0.record()
     dbg = [] if os.environ.get("BENCH_DEBUG_EVENTS") else None
+    rpipe.begin()
     for _ in range(args.steps):
-        step()
+        rpipe.enqueue_step(x0, x_out)
         if dbg is not None:
             dbg.append(torch.cuda.Event(enable_timing=True))
             dbg[-1].record()
+    rpipe.end()
     if dbg is not None:
         torch.cuda.synchronize(dev)
         ts = [e0.elapsed_time(dbg[0])] + [dbg[i].elapsed_time(dbg[i + 1]) for i in range(len(dbg) - 1)]
@@ -361,6 +377,16 @@ def main():
     e2e_value = world * evals_per_step / (e2e_ms / e2e_steps * 1e-3)
     h2d = x_host.numel() * 4
     d2h = out_host.numel() * 4
+
+    # ---- the same iteration on ONE stream (assembly and solve back to back), for comparison
+    n_single = max(5, min(args.steps, 100))
+    barrier()
+    e0.record()
+    for _ in range(n_single):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_single = e0.elapsed_time(e1) / n_single
 
     # ---- per-kernel durations (live, CUDA events on the launching stream) for the roofline
     n_prof = max(5, min(args.steps, 50))
@@ -425,7 +451,7 @@ def main():
     }
     solve_bytes = 3 * ws_bytes + 2 * x0.numel() * 4  # read blocks, write (S^-1,u), read them back; read q, write x
     roofline_solve = {
-        "kernel": "lm_block_solve_kernel<Fetch> (twisted block-Thomas sweep, two lanes per path, TMA bulk-copy block streaming)",
+        "kernel": "lm_block_solve_kernel<Fetch> (twisted block-Thomas sweep, two lanes per path, TMA bulk-copy block loads)",
         "bound": "hbm",
         "achieved": solve_bytes / (ms_solve * 1e-3) / 1e9,
         "peak": hbm_peak,
@@ -484,7 +510,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": "waypoint-evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": wall / e2e_steps * 1e3, "steps": e2e_steps,
                 "api": "cppflow_b200.pipeline.HostPipeline.refine(host x -> host x_new), pinned host buffers"},
-        "gpu_launches": args.steps * 2 + 1,
+        "gpu_launches": args.steps * 2 * len(rpipe.chunks) + 1,
+        "single_stream_ms_per_step": ms_single,
         "roofline": roofline,
         "roofline_solve": roofline_solve,
         "roofline_step": roofline_step,

@@ -23,7 +23,7 @@ from .lm_hyper_parameters import OptimizationParameters, all_terms_parameters
 
 class HostPipeline:
     def __init__(self, problem: Problem, n_paths: int, params: Optional[OptimizationParameters] = None,
-                 n_chunks: int = 16, n_run_streams: int = 4, device=None, use_graph: bool = True):
+                 n_chunks: int = 16, n_run_streams: int = 4, device=None, use_graph: bool = True, overlap: bool = True):
         self.problem = problem
         self.robot = problem.robot
         self.T = problem.n_timesteps
@@ -49,7 +49,8 @@ class HostPipeline:
         lib_bytes = ops._lib.load().cppflow_lm_full_workspace_bytes(self.robot.robot_id, max(n for _, n in self.chunks), self.T)
         self.ws = [torch.empty((lib_bytes,), device=self.device, dtype=torch.uint8) for _ in self.s_run]
         self.use_graph = use_graph
-        self._graphs = {}
+        self.flags = ops.LM_CLAMP | (ops.LM_OVERLAP if overlap else 0)  # overlap: the solve of a chunk runs under the
+        self._graphs = {}                                              # assembly of the next (see ResidentPipeline)
 
     def refine(self, x_host: torch.Tensor, out_host: torch.Tensor) -> torch.Tensor:
         """One fused LM iteration (+ clamp) over all paths: x_host [P*T, D] pinned -> out_host [P*T, D] pinned.
@@ -87,7 +88,7 @@ class HostPipeline:
                 s_run.wait_event(self.ev_in[c])
                 ws = self.ws[c % len(self.s_run)]
                 ops.check(lib.cppflow_lm_full_step(
-                    rid, self.prm, ops.ptr(self.x_dev[sl]), None, ops.ptr(self.problem.target_path), n, T, cu, tc, no, 1,
+                    rid, self.prm, ops.ptr(self.x_dev[sl]), None, ops.ptr(self.problem.target_path), n, T, cu, tc, no, self.flags,
                     ops.ptr(ws), ws.numel(), ops.ptr(self.out_dev[sl]), ops.stream_ptr(self.device)))
                 self.ev_run[c].record(s_run)
             with torch.cuda.stream(self.s_out):

@@ -22,7 +22,7 @@ def timeit(fn,n=40):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1)/n
-names={'-':'default deep 6,2,4w / compact 3,1,4w','a':'3,0,4w','b':'2,0,4w','c':'2,0,8w','d':'3,1,4w','e':'6,0,4w','f':'4,0,4w'}
+names={'-':'default ring3 alone / ring4 overlap, 4w, q smem','a':'ring3 4w qreg','b':'ring4 4w qreg','c':'ring3 6w qreg','d':'ring5 4w qreg','e':'ring2 8w qreg'}
 for var in sys.argv[1:] or list(names):
     if var=='-': os.environ.pop('CPPFLOW_DEBUG_SOLVE_VARIANT',None)
     else: os.environ['CPPFLOW_DEBUG_SOLVE_VARIANT']=var
