@@ -55,7 +55,29 @@ class RobotInfoC(C.Structure):
     ]
 
 
-_VP, _I, _I64, _SZ, _F = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float
+class ConstraintsC(C.Structure):
+    """cppflow_constraints"""
+
+    _fields_ = [
+        ("max_allowed_position_error_cm", C.c_float),
+        ("max_allowed_rotation_error_deg", C.c_float),
+        ("max_allowed_mjac_deg", C.c_float),
+        ("max_allowed_mjac_cm", C.c_float),
+    ]
+
+
+class LmLoopResultC(C.Structure):
+    """cppflow_lm_loop_result"""
+
+    _fields_ = [
+        ("n_steps_taken", C.c_int32),
+        ("is_valid", C.c_int32),
+        ("last_metrics", C.c_float * 8),
+        ("schedule", C.c_char * 256),
+    ]
+
+
+_VP, _I, _I64, _SZ, _F, _DBL = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float, C.c_double
 _PROTOTYPES = {
     # name: (restype, argtypes)
     "cppflow_version": (C.c_char_p, []),
@@ -75,6 +97,10 @@ _PROTOTYPES = {
     "cppflow_lm_full_assemble": (_I, [_I, C.POINTER(LmParamsC), _VP, _VP, _VP, _I64, _I64, c_float_p, c_float_p, _I, _VP,
                                       _SZ, _VP]),
     "cppflow_lm_full_solve": (_I, [_I, C.POINTER(LmParamsC), _VP, _I64, _I64, _I, _VP, _SZ, _VP, _VP]),
+    "cppflow_lm_alternating_workspace_bytes": (_SZ, [_I, _I64]),
+    "cppflow_lm_alternating_loss": (_I, [_I, C.POINTER(LmParamsC), C.POINTER(LmParamsC), C.POINTER(ConstraintsC), _VP, _VP,
+                                         _I64, c_float_p, c_float_p, _I, _I, _DBL, _I, _DBL, _VP, _SZ, _VP, _VP,
+                                         C.POINTER(LmLoopResultC), _VP]),
     "cppflow_joint_limit_flags": (_I, [_I, _VP, _I64, _F, _F, _VP, _VP]),
     "cppflow_dp_search_workspace_bytes": (_SZ, [_I64, _I64]),
     "cppflow_dp_search": (_I, [_I, _VP, _VP, _VP, _I64, _I64, _VP, _SZ, _VP, _VP, _VP, _VP, _VP]),

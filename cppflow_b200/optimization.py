@@ -115,8 +115,12 @@ def run_lm_alternating_loss(opt_problem: OptimizationProblem, opt_state: Optimiz
                             params_diff: OptimizationParameters, params_pose: OptimizationParameters,
                             return_residuals: bool, tmax_sec: float, max_n_steps: int,
                             return_if_valid_after_n_steps: int, convergence_threshold: float, verbosity: int = 0,
-                            save_images: bool = False, results_df: Optional[Dict] = None, mesh_validator=None):
-    """Control flow of optimization.py:147-373 for ONE path (parallel_count == 1)."""
+                            save_images: bool = False, results_df: Optional[Dict] = None, mesh_validator=None,
+                            native: bool = True):
+    """Control flow of optimization.py:147-373 for ONE path (parallel_count == 1).  Without a mesh validator the loop
+    runs inside the library (csrc/lm_loop.cu: same decisions, ~10 us of host time per iteration);
+    `run_lm_alternating_loss_python` is the same loop in Python, kept for the mesh-validator callback, for
+    verbosity > 1 and as the cross-check of the native loop (tests/test_gpu_planner.py)."""
     assert opt_problem.parallel_count == 1, "the alternating loop is per path; batch with run_lm_fixed_schedule"
     assert not save_images and not return_residuals, "debug outputs of the reference are not reproduced"
     if tmax_sec is None:
@@ -126,6 +130,22 @@ def run_lm_alternating_loss(opt_problem: OptimizationProblem, opt_state: Optimiz
     if max_n_steps is None:
         assert tmax_sec is not None
         max_n_steps = int(1e9)
+    if native and mesh_validator is None and verbosity <= 1 and not (SELF_COLLISIONS_IGNORED or ENV_COLLISIONS_IGNORED):
+        problem, robot = opt_problem.problem, opt_problem.robot
+        x_opt, n_steps, is_valid, schedule, _ = ops.lm_alternating_loss(
+            robot.robot_id, robot.ndof, ops.make_params(params_diff), ops.make_params(params_pose),
+            opt_problem.constraints, opt_state.x, problem.target_path, problem.n_timesteps, problem.obstacle_tables,
+            min(max_n_steps, 2 ** 31 - 1), tmax_sec, min(return_if_valid_after_n_steps, 2 ** 31 - 1), convergence_threshold)
+        return OptimizationResult(x_opt=x_opt, n_steps_taken=n_steps, is_valid=is_valid, parallel_seed_idx=0,
+                                  schedule=schedule)
+    return run_lm_alternating_loss_python(opt_problem, opt_state, params_diff, params_pose, tmax_sec, max_n_steps,
+                                          return_if_valid_after_n_steps, convergence_threshold, verbosity, mesh_validator)
+
+
+def run_lm_alternating_loss_python(opt_problem: OptimizationProblem, opt_state: OptimizationState,
+                                   params_diff: OptimizationParameters, params_pose: OptimizationParameters,
+                                   tmax_sec: float, max_n_steps: int, return_if_valid_after_n_steps: int,
+                                   convergence_threshold: float, verbosity: int = 0, mesh_validator=None):
     problem = opt_problem.problem
 
     def printc(*args, **kwargs):
@@ -195,7 +215,8 @@ def run_lm_alternating_loss(opt_problem: OptimizationProblem, opt_state: Optimiz
 
 def run_lm_optimization(problem: Problem, x_seed: torch.Tensor, tmax_sec: float, max_n_steps: int,
                         return_if_valid_after_n_steps: int, convergence_threshold: float, parallel_count: int = 1,
-                        results_df: Optional[Dict] = None, verbosity: int = 1, mesh_validator=None) -> OptimizationResult:
+                        results_df: Optional[Dict] = None, verbosity: int = 1, mesh_validator=None,
+                        native: bool = True) -> OptimizationResult:
     """Optimise a trajectory (optimization.py:376-426)."""
     if SELF_COLLISIONS_IGNORED:
         warnings.warn("robot-robot are collisions will be ignored during LM optimization")
@@ -215,5 +236,5 @@ def run_lm_optimization(problem: Problem, x_seed: torch.Tensor, tmax_sec: float,
         opt_problem, opt_state, ALT_LOSS_V2_1_DIFF, ALT_LOSS_V2_1_POSE, return_residuals=False, verbosity=verbosity,
         tmax_sec=tmax_sec, max_n_steps=max_n_steps, return_if_valid_after_n_steps=return_if_valid_after_n_steps,
         convergence_threshold=convergence_threshold, save_images=False, results_df=results_df,
-        mesh_validator=mesh_validator,
+        mesh_validator=mesh_validator, native=native,
     )

@@ -147,6 +147,36 @@ int cppflow_lm_full_solve(int robot, const cppflow_lm_params* params, const floa
 #define CPPFLOW_LM_CLAMP 1
 #define CPPFLOW_LM_OVERLAP 2
 
+/* run_lm_alternating_loss for ONE path (optimization.py:147-373; called by run_lm_optimization :376-426 with
+ * ALT_LOSS_V2_1_DIFF / ALT_LOSS_V2_1_POSE): pose-only steps until the position and rotation errors are inside the
+ * constraints, joint-differencing steps otherwise, clamp after every step, convergence on the trajectory length after
+ * differencing steps, the last valid iterate is returned (the current one if none was valid).  Validity = the
+ * thresholds of evaluation_utils.py:29-75 (strict <) and non-negative capsule distances (the reference's klampt mesh
+ * checks, optimization_utils.py:889-900, are out of scope; the Python host keeps a loop with a mesh callback).
+ * UNLIKE the other entry points this one BLOCKS: like the reference (`.item()`, :175) it reads the metrics of every
+ * iterate on the host - 8 floats into `h_pinned_metrics` (page-locked host memory) and one cudaStreamSynchronize per
+ * iteration.  Workspace: cppflow_lm_alternating_workspace_bytes(robot, T) bytes, 256-byte aligned. */
+typedef struct cppflow_constraints { /* data_types.py:53-62 */
+    float max_allowed_position_error_cm;
+    float max_allowed_rotation_error_deg;
+    float max_allowed_mjac_deg;
+    float max_allowed_mjac_cm;
+} cppflow_constraints;
+#define CPPFLOW_LM_SCHEDULE_MAX 256
+typedef struct cppflow_lm_loop_result { /* OptimizationResult, optimization.py:52-57 */
+    int32_t n_steps_taken;
+    int32_t is_valid;
+    float last_metrics[8];                  /* cppflow_path_metrics row of the last iterate examined */
+    char schedule[CPPFLOW_LM_SCHEDULE_MAX]; /* step types taken: 'p' pose-only, 'd' differencing; 0-terminated */
+} cppflow_lm_loop_result;
+size_t cppflow_lm_alternating_workspace_bytes(int robot, int64_t T);
+int cppflow_lm_alternating_loss(int robot, const cppflow_lm_params* params_diff, const cppflow_lm_params* params_pose,
+                                const cppflow_constraints* constraints, const float* d_x_seed, const float* d_target,
+                                int64_t T, const float* h_cuboids, const float* h_Tcuboids, int n_obstacles,
+                                int max_n_steps, double tmax_sec, int return_if_valid_after_n_steps,
+                                double convergence_threshold, void* d_workspace, size_t workspace_bytes,
+                                float* h_pinned_metrics, float* d_x_out, cppflow_lm_loop_result* result, void* stream);
+
 /* joint_limit_almost_violations_3d(robot, qs, eps_revolute, eps_prismatic) -> float32 0/1 [n]  (search.py:25-52) */
 int cppflow_joint_limit_flags(int robot, const float* d_q, int64_t n, float eps_revolute, float eps_prismatic,
                               float* d_flags, void* stream);

@@ -97,9 +97,9 @@ def test_config4_all_problems_planner_runs():
     """BASELINE config 4: all 13 benchmark problems through CppFlowPlanner (dp_search + alternating LM loop).  The
     returned path has the problem's shape, stays inside the joint limits and tracks the target path: the pose
     constraints of scripts/evaluate.py:51-56 (0.1 mm / 0.1 deg) hold whenever the planner reports a valid plan, and a
-    valid plan is found for most problems.  (The candidates come from the stand-in generator, not IKFlow: from random
-    seeds its LM-IK reaches the target on only ~25 % of the waypoints, and for the Panda problems almost never, so
-    "most" is 9 of 13 at k = 175 today - the bar below leaves two problems of slack.)"""
+    valid plan is found for most problems.  (The candidates come from the stand-in generator, not IKFlow: its damped
+    LM-IK from random seeds reaches the target on 30-90 % of the waypoints; 12 of 13 problems end with a valid plan at
+    k = 175 today - panda__flappy_bird does not - and the bar below leaves two problems of slack.)"""
     from cppflow_b200.data_type_utils import ALL_PROBLEM_FILENAMES
     from cppflow_b200.data_types import PlannerSettings
     from cppflow_b200.planners import CppFlowPlanner, LmIkCandidateGenerator
@@ -128,5 +128,48 @@ def test_config4_all_problems_planner_runs():
             ref = L.path_metrics(m, q.cpu().double(), problem.target_path.cpu().double(),
                                  [t.double() for t in Tcuboids], [cb.double() for cb in cuboids])
             assert abs(float(ref["max_pos_cm"]) - res.plan.max_pos_error_cm) < 1e-3, name
-            assert abs(float(ref["max_rot_deg"]) - res.plan.max_rot_error_deg) < 1e-2, name
-    assert n_valid >= 7, f"only {n_valid} valid plans"
+            # fp32 geodesic distance 2 acos(min(|dot|, 1 - 1e-7)) is quantised near zero (0.056, 0.069, 0.079 deg ...: one
+            # ulp of the dot product per step), as the reference's own fp32 evaluation is; the oracle runs in fp64
+            assert abs(float(ref["max_rot_deg"]) - res.plan.max_rot_error_deg) < 3e-2, name
+    assert n_valid >= 10, f"only {n_valid} valid plans"
+
+
+@pytest.mark.parametrize("name", ["fetch__circle", "fetch_arm__s", "panda__2cubes", "fetch__hello"])
+def test_native_alternating_loop_equals_python_loop(name):
+    """cppflow_lm_alternating_loss (csrc/lm_loop.cu) takes the decisions of run_lm_alternating_loss
+    (optimization.py:147-373) in C++: same step sequence, same iterate returned (bit-identical), same n_steps_taken /
+    is_valid as the Python transcription of the loop, in both of the planner's call patterns (planners.py:402-422)."""
+    from cppflow_b200.optimization import run_lm_optimization
+    from cppflow_b200.planners import LmIkCandidateGenerator
+    from cppflow_b200.collision_detection import qpaths_batched_collisions
+    from cppflow_b200.search import dp_search
+
+    problem = _problem(name)
+    qs = LmIkCandidateGenerator(seed=1)(problem, 64).contiguous()
+    self_v, env_v = qpaths_batched_collisions(problem, qs)
+    seed = dp_search(problem.robot, qs, self_v, env_v, verbosity=0).to(DEV).contiguous()
+    for kw in (dict(max_n_steps=20, return_if_valid_after_n_steps=0, convergence_threshold=1e6),
+               dict(max_n_steps=30, return_if_valid_after_n_steps=int(1e8), convergence_threshold=0.005),
+               dict(max_n_steps=1, return_if_valid_after_n_steps=0, convergence_threshold=1e6)):
+        a = run_lm_optimization(problem, seed, tmax_sec=30.0, verbosity=0, native=True, **kw)
+        b = run_lm_optimization(problem, seed, tmax_sec=30.0, verbosity=0, native=False, **kw)
+        assert a.schedule == b.schedule and len(a.schedule) >= 1, (name, kw, a.schedule, b.schedule)
+        assert a.n_steps_taken == b.n_steps_taken and a.is_valid == b.is_valid, (name, kw)
+        assert torch.equal(a.x_opt, b.x_opt), (name, kw)
+
+
+def test_path_metrics_cluster_split_matches_single_cta():
+    """Few paths: a path's waypoints are split over the CTAs of a thread-block cluster; many paths: one CTA per path.
+    Maxima / minima are identical, the trajectory-length sum differs only by the order of the additions."""
+    from cppflow_b200 import ops
+    from cppflow_b200.planners import LmIkCandidateGenerator
+
+    problem = _problem("fetch__circle")
+    rob, T = problem.robot, problem.n_timesteps
+    qs = LmIkCandidateGenerator(seed=5)(problem, 400).contiguous()  # 400 paths: one CTA per path
+    many = ops.path_metrics(rob.robot_id, rob.ndof, qs.reshape(-1, rob.ndof), problem.target_path, 400, T,
+                            problem.obstacle_tables)
+    for p in (0, 7, 399):  # one path: cluster of 3 CTAs
+        one = ops.path_metrics(rob.robot_id, rob.ndof, qs[p].contiguous(), problem.target_path, 1, T, problem.obstacle_tables)
+        assert torch.equal(one[0, [0, 1, 2, 3, 5, 6]], many[p, [0, 1, 2, 3, 5, 6]]), p
+        assert abs(float(one[0, 4]) - float(many[p, 4])) <= 1e-5 * float(many[p, 4]), p
