@@ -308,8 +308,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+// arrival count 1: the thread that arms the barrier with expect_tx
+__device__ __forceinline__ void mbar_init(uint64_t* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -332,7 +333,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned 
 }
 // per-warp shared memory: SOLVE_RING load slots, each holding the two blocks of one step
 // (side 1's block is shifted by 64 B so that the LDS.128 of the two sides hit different banks), the q rows of
-// the back-substitution, and one mbarrier per load slot
+// the back-substitution (the mbarriers of the load slots are static shared memory)
 template <int D, int SOLVE_RING>
 struct SolveSmem {
     static constexpr int NV = BlockLayout<D>::NW / 4;                      // float4 per block
@@ -340,8 +341,7 @@ struct SolveSmem {
     static constexpr int SLOT_BYTES = (2 * BLK_BYTES + 64 + 127) / 128 * 128;
     static constexpr int Q_BYTES = ((D + 3) / 4) * 16 * 32;                // q rows of one step, 32 lanes
     static constexpr int OFF_Q = SOLVE_RING * SLOT_BYTES;
-    static constexpr int OFF_BAR = OFF_Q + SOLVE_RING * Q_BYTES;
-    static constexpr int BYTES = (OFF_BAR + SOLVE_RING * 8 + 127) / 128 * 128;
+    static constexpr int BYTES = (OFF_Q + SOLVE_RING * Q_BYTES + 127) / 128 * 128;
     __device__ static unsigned char* part(unsigned char* slot, int side) { return slot + side * (BLK_BYTES + 64); }
     // float4 k of path l (0..15) of the block held in `part`
     __device__ static float4* blk(unsigned char* part, int k, int l) { return reinterpret_cast<float4*>(part) + k * 16 + l; }
@@ -379,9 +379,16 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
     extern __shared__ __align__(128) unsigned char smem_all[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t g = (int64_t)blockIdx.x * SOLVE_WARPS + warp;  // 16-path group of this warp
-    if (g * 16 >= P) return;                                     // warps are independent: no block-level sync below
+    __shared__ uint64_t s_bars[SOLVE_WARPS][SOLVE_RING];  // one mbarrier per load slot
+    uint64_t* bars = s_bars[warp];
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < SOLVE_RING; ++j) mbar_init(bars + j);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();          // the only block-level synchronisation: warps are independent from here on
+    if (g * 16 >= P) return;
     unsigned char* sm = smem_all + (size_t)warp * SM::BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM::OFF_BAR);
     const int side = lane & 1, l = lane >> 1;
     const int64_t p_raw = g * 16 + l;
     const bool active = p_raw < P;
@@ -393,13 +400,6 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
     const int64_t n_side = side == 0 ? n0 : n1;
     const int64_t n_iter = n0 > n1 ? n0 : n1;
     const BetaSel<M> bs(prm.b_rev, prm.b_pri);
-
-    if (lane == 0) {
-#pragma unroll
-        for (int j = 0; j < SOLVE_RING; ++j) mbar_init(bars + j, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
 
     // lane 0: arm slot (s % RING) and fetch the blocks t0 (side 0) / t1 (side 1); a negative t skips that side
     // `token` is the (always zero, but opaque to the compiler) value of slot_read_token below: folding it into the
