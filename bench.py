@@ -206,6 +206,43 @@ def plan_latency_gpu(dev, k=175, reps=10):
     }, problem, qs.cpu()
 
 
+def plan_all_problems_gpu(dev, k=175, reps=5):
+    """BASELINE config 4: the 13 benchmark problems (candidate generation included), one after the other and
+    concurrently (planners.plan_many: one CUDA stream per problem, stages phase by phase, LM loops in lock step).  Host wall clock, median."""
+    from cppflow_b200.data_type_utils import ALL_PROBLEM_FILENAMES, problem_from_filename
+    from cppflow_b200.data_types import PlannerSettings
+    from cppflow_b200.planners import CppFlowPlanner, LmIkCandidateGenerator, plan_many
+
+    problems = [problem_from_filename(None, name, device=dev) for name in ALL_PROBLEM_FILENAMES]
+
+    def factory(problem):
+        return CppFlowPlanner(PlannerSettings(k=k, tmax_sec=30.0, anytime_mode_enabled=False, verbosity=0), problem.robot,
+                              LmIkCandidateGenerator(seed=1))
+
+    def sequential():
+        return [factory(p).generate_plan(p) for p in problems]
+
+    def batched():
+        return plan_many(factory, problems)
+
+    out = {}
+    for name, fn in (("sequential_ms", sequential), ("batched_ms", concurrent)):
+        fn()
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            res = fn()
+            torch.cuda.synchronize(dev)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        out[name] = statistics.median(ts)
+    out.update({"problems": len(problems), "k": k, "waypoints_total": sum(p.n_timesteps for p in problems),
+                "valid_plans": sum(bool(r.plan.is_valid) for r in res),
+                "what": "CppFlowPlanner.generate_plan on all 13 benchmark problems: stand-in candidate generation + "
+                        "collision flags + dp_search + alternating LM loop (max 20 steps, return once valid)"})
+    return out
+
+
 def plan_latency_cpu(problem, qs, schedule):
     """The same plan through the oracle port of the reference's torch path on the host cores (the LM loop replays the
     step types the GPU run took; the reference's per-step klampt validity check is not included)."""
@@ -477,7 +514,9 @@ def main():
         return
 
     plan = None
+    plan_all = None
     if world == 1:
+        plan_all = plan_all_problems_gpu(dev)
         plan, plan_problem, plan_qs = plan_latency_gpu(dev)
         if not args.no_cpu_baseline:
             plan["cpu_baseline"] = plan_latency_cpu(plan_problem, plan_qs, plan["schedule"])
@@ -518,6 +557,7 @@ def main():
         "kernel_ms": {"lm_assemble_kernel": ms_assemble, "lm_block_solve_kernel": ms_solve},
         "cpu_baseline": cpu_baseline,
         "plan_latency": plan,
+        "plan_all_problems": plan_all,
         "argmin": {"cost": best_cost, "rank": best_rank, "path": best_idx},
     }
     emit(line)

@@ -77,6 +77,33 @@ class LmLoopResultC(C.Structure):
     ]
 
 
+class LmLoopJobC(C.Structure):
+    """cppflow_lm_loop_job"""
+
+    _fields_ = [
+        ("robot", C.c_int32),
+        ("params_diff", C.POINTER(LmParamsC)),
+        ("params_pose", C.POINTER(LmParamsC)),
+        ("constraints", C.POINTER(ConstraintsC)),
+        ("d_x_seed", C.c_void_p),
+        ("d_target", C.c_void_p),
+        ("T", C.c_int64),
+        ("h_cuboids", c_float_p),
+        ("h_Tcuboids", c_float_p),
+        ("n_obstacles", C.c_int32),
+        ("max_n_steps", C.c_int32),
+        ("tmax_sec", C.c_double),
+        ("return_if_valid_after_n_steps", C.c_int32),
+        ("convergence_threshold", C.c_double),
+        ("d_workspace", C.c_void_p),
+        ("workspace_bytes", C.c_size_t),
+        ("h_pinned_metrics", C.c_void_p),
+        ("d_x_out", C.c_void_p),
+        ("result", C.POINTER(LmLoopResultC)),
+        ("stream", C.c_void_p),
+    ]
+
+
 _VP, _I, _I64, _SZ, _F, _DBL = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float, C.c_double
 _PROTOTYPES = {
     # name: (restype, argtypes)
@@ -101,6 +128,7 @@ _PROTOTYPES = {
     "cppflow_lm_alternating_loss": (_I, [_I, C.POINTER(LmParamsC), C.POINTER(LmParamsC), C.POINTER(ConstraintsC), _VP, _VP,
                                          _I64, c_float_p, c_float_p, _I, _I, _DBL, _I, _DBL, _VP, _SZ, _VP, _VP,
                                          C.POINTER(LmLoopResultC), _VP]),
+    "cppflow_lm_alternating_loss_many": (_I, [_I, C.POINTER(LmLoopJobC)]),
     "cppflow_joint_limit_flags": (_I, [_I, _VP, _I64, _F, _F, _VP, _VP]),
     "cppflow_dp_search_workspace_bytes": (_SZ, [_I64, _I64]),
     "cppflow_dp_search": (_I, [_I, _VP, _VP, _VP, _I64, _I64, _VP, _SZ, _VP, _VP, _VP, _VP, _VP]),

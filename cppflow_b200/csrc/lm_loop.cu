@@ -10,6 +10,7 @@
 // (the per-plan latency of fetch__circle is dominated by these 20 round trips, not by the kernels).
 #include <chrono>
 #include <cmath>
+#include <vector>
 
 #include "common.cuh"
 
@@ -22,6 +23,7 @@ inline size_t align256(size_t n) { return (n + 255) / 256 * 256; }
 struct LoopLayout {
     size_t x_bytes, off_xa, off_xb, off_valid, off_metrics, off_lm, total;
     LoopLayout(int robot, int ndof, int64_t T) {
+        if (ndof <= 0) { x_bytes = off_xa = off_xb = off_valid = off_metrics = off_lm = total = 0; return; }
         x_bytes = align256((size_t)T * ndof * sizeof(float));
         off_xa = 0;
         off_xb = off_xa + x_bytes;
@@ -46,6 +48,147 @@ extern "C" size_t cppflow_lm_alternating_workspace_bytes(int robot, int64_t T) {
     return LoopLayout(robot, ndof, T).total;
 }
 
+namespace {
+
+// One path's alternating loop as a state machine: launch() enqueues the next step, the metrics kernel and the
+// device -> host copy of the 8 metrics on the job's stream; finish() waits for them and takes the reference's decisions.
+// The single-path entry point runs launch/finish in turn; the many-path entry point launches the step of EVERY active
+// job before it waits for any of them, so independent problems overlap on the device.
+struct LoopState {
+    const cppflow_lm_loop_job* job = nullptr;
+    LoopLayout L{0, 0, 1};
+    int ndof = 0;
+    float *x_cur = nullptr, *x_new = nullptr, *x_valid = nullptr, *d_metrics = nullptr;
+    void* lm_ws = nullptr;
+    size_t lm_ws_bytes = 0, row_bytes = 0;
+    bool pose_pos_valid = true, pose_rot_valid = false;  // the reference starts (True, False): first step pose-only (:219-220)
+    bool converged = false, has_valid = false, was_differencing = false, done = false;
+    int last_valid_idx = -1, n_tls = 0, i = 0, n_sched = 0;
+    double last_tl = 0.0;
+    std::chrono::steady_clock::time_point t0;
+
+    int init(const cppflow_lm_loop_job* j) {
+        job = j;
+        if (!(j->params_diff && j->params_pose && j->constraints && j->result)) return fail(CPPFLOW_E_INVALID, "lm_alternating_loss: null parameter struct");
+        if (!(j->d_x_seed && j->d_target && j->d_x_out && j->d_workspace && j->h_pinned_metrics)) return fail(CPPFLOW_E_INVALID, "lm_alternating_loss: null pointer");
+        if (!(j->T > 0 && j->max_n_steps >= 0)) return fail(CPPFLOW_E_INVALID, "lm_alternating_loss: T, max_n_steps");
+        ndof = robot_ndof(j->robot);
+        if (ndof < 0) return CPPFLOW_E_INVALID;
+        L = LoopLayout(j->robot, ndof, j->T);
+        if (j->workspace_bytes < L.total)
+            return fail(CPPFLOW_E_WORKSPACE, "lm_alternating_loss: workspace too small (%zu < %zu)", j->workspace_bytes, L.total);
+        if (((uintptr_t)j->d_workspace & 255) != 0) return fail(CPPFLOW_E_INVALID, "lm_alternating_loss: workspace must be 256-byte aligned");
+        unsigned char* ws = (unsigned char*)j->d_workspace;
+        x_cur = (float*)(ws + L.off_xa);
+        x_new = (float*)(ws + L.off_xb);
+        x_valid = (float*)(ws + L.off_valid);
+        d_metrics = (float*)(ws + L.off_metrics);
+        lm_ws = ws + L.off_lm;
+        lm_ws_bytes = L.total - L.off_lm;
+        row_bytes = (size_t)j->T * ndof * sizeof(float);
+        cudaError_t e = cudaMemcpyAsync(x_cur, j->d_x_seed, row_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)j->stream);
+        if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "lm_alternating_loss: %s", cudaGetErrorString(e));
+        t0 = std::chrono::steady_clock::now();
+        done = j->max_n_steps == 0;
+        return CPPFLOW_OK;
+    }
+
+    int launch() {
+        const cppflow_lm_loop_job* j = job;
+        if (pose_pos_valid && pose_rot_valid) {
+            // virtual configs = the current iterate (:253): their residual is identically zero -> d_xv = NULL
+            if (int rc = cppflow_lm_full_step(j->robot, j->params_diff, x_cur, nullptr, j->d_target, 1, j->T, j->h_cuboids,
+                                              j->h_Tcuboids, j->n_obstacles, CPPFLOW_LM_CLAMP, lm_ws, lm_ws_bytes, x_new, j->stream))
+                return rc;
+            was_differencing = true;
+        } else {
+            if (int rc = cppflow_lm_pose_step(j->robot, j->params_pose, x_cur, j->d_target, j->T, j->T, 1, x_new, nullptr, nullptr, j->stream))
+                return rc;
+            was_differencing = false;
+        }
+        if (n_sched < CPPFLOW_LM_SCHEDULE_MAX - 1) j->result->schedule[n_sched++] = was_differencing ? 'd' : 'p';
+        float* tmp = x_cur; x_cur = x_new; x_new = tmp;  // clamp_to_joint_limits is fused into both steps (:259)
+        if (int rc = cppflow_path_metrics(j->robot, x_cur, j->d_target, 1, j->T, j->h_cuboids, j->h_Tcuboids, j->n_obstacles,
+                                          d_metrics, j->stream))
+            return rc;
+        cudaError_t e = cudaMemcpyAsync(j->h_pinned_metrics, d_metrics, 8 * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)j->stream);
+        if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "lm_alternating_loss: %s", cudaGetErrorString(e));
+        return CPPFLOW_OK;
+    }
+
+    int finish() {
+        const cppflow_lm_loop_job* j = job;
+        cudaError_t e = cudaStreamSynchronize((cudaStream_t)j->stream);  // the one host round trip of the iteration
+        if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "lm_alternating_loss: %s", cudaGetErrorString(e));
+        const float* m = j->h_pinned_metrics;  // max_pos_cm, max_rot_deg, mjac_deg, mjac_cm, tl, min_self, min_env
+        const double tl_new = m[4];
+        if (was_differencing) {
+            if (!converged && n_tls > 0) {
+                if (std::fabs(tl_new - last_tl) < j->convergence_threshold) {
+                    converged = true;
+                    if (last_valid_idx == i - 1) { done = true; return CPPFLOW_OK; }
+                }
+            }
+            last_tl = tl_new;
+            ++n_tls;
+        }
+        // x_is_valid (:836-923): strict '<' thresholds (evaluation_utils.py:29-75), then the collision check
+        const cppflow_constraints* c = j->constraints;
+        pose_pos_valid = m[0] < c->max_allowed_position_error_cm;
+        pose_rot_valid = m[1] < c->max_allowed_rotation_error_deg;
+        const bool mjac_ok = m[2] < c->max_allowed_mjac_deg && m[3] < c->max_allowed_mjac_cm;
+        const bool is_valid = pose_pos_valid && pose_rot_valid && mjac_ok && !(m[5] < 0.f) && !(m[6] < 0.f);
+        if (is_valid) {
+            last_valid_idx = i;
+            has_valid = true;
+            e = cudaMemcpyAsync(x_valid, x_cur, row_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)j->stream);
+            if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "lm_alternating_loss: %s", cudaGetErrorString(e));
+            if (converged) { done = true; return CPPFLOW_OK; }
+        }
+        const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (elapsed > j->tmax_sec) { done = true; return CPPFLOW_OK; }
+        if (has_valid && (i > j->return_if_valid_after_n_steps || i > j->max_n_steps)) { done = true; return CPPFLOW_OK; }
+        if (i + 1 >= j->max_n_steps) { done = true; return CPPFLOW_OK; }  // Python's range() exhausted: i stays at the last value
+        ++i;
+        return CPPFLOW_OK;
+    }
+
+    int finalize() {
+        const cppflow_lm_loop_job* j = job;
+        cudaError_t e = cudaMemcpyAsync(j->d_x_out, has_valid ? x_valid : x_cur, row_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)j->stream);
+        if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "lm_alternating_loss: %s", cudaGetErrorString(e));
+        j->result->schedule[n_sched] = 0;
+        j->result->n_steps_taken = i;
+        j->result->is_valid = has_valid ? 1 : 0;
+        for (int k = 0; k < 8; ++k) j->result->last_metrics[k] = j->max_n_steps > 0 ? j->h_pinned_metrics[k] : 0.f;
+        return CPPFLOW_OK;
+    }
+};
+
+}  // namespace
+
+extern "C" int cppflow_lm_alternating_loss_many(int n_jobs, const cppflow_lm_loop_job* jobs) {
+    CPPFLOW_CHECK_ARG(n_jobs >= 0 && (n_jobs == 0 || jobs != nullptr), "jobs");
+    std::vector<LoopState> st((size_t)n_jobs);
+    for (int k = 0; k < n_jobs; ++k)
+        if (int rc = st[k].init(&jobs[k])) return rc;
+    for (;;) {
+        int n_active = 0;
+        for (int k = 0; k < n_jobs; ++k)
+            if (!st[k].done) {
+                if (int rc = st[k].launch()) return rc;
+                ++n_active;
+            }
+        if (n_active == 0) break;
+        for (int k = 0; k < n_jobs; ++k)
+            if (!st[k].done)
+                if (int rc = st[k].finish()) return rc;
+    }
+    for (int k = 0; k < n_jobs; ++k)
+        if (int rc = st[k].finalize()) return rc;
+    return CPPFLOW_OK;
+}
+
 extern "C" int cppflow_lm_alternating_loss(int robot, const cppflow_lm_params* params_diff,
                                            const cppflow_lm_params* params_pose, const cppflow_constraints* constraints,
                                            const float* d_x_seed, const float* d_target, int64_t T,
@@ -54,95 +197,26 @@ extern "C" int cppflow_lm_alternating_loss(int robot, const cppflow_lm_params* p
                                            double convergence_threshold, void* d_workspace, size_t workspace_bytes,
                                            float* h_pinned_metrics, float* d_x_out, cppflow_lm_loop_result* result,
                                            void* stream) {
-    CPPFLOW_CHECK_ARG(params_diff && params_pose && constraints && result, "null parameter struct");
-    CPPFLOW_CHECK_ARG(d_x_seed && d_target && d_x_out && d_workspace && h_pinned_metrics, "null pointer");
-    CPPFLOW_CHECK_ARG(T > 0 && max_n_steps >= 0, "T, max_n_steps");
-    const int ndof = robot_ndof(robot);
-    if (ndof < 0) return CPPFLOW_E_INVALID;
-    const LoopLayout L(robot, ndof, T);
-    if (workspace_bytes < L.total)
-        return fail(CPPFLOW_E_WORKSPACE, "lm_alternating_loss: workspace too small (%zu < %zu)", workspace_bytes, L.total);
-    CPPFLOW_CHECK_ARG(((uintptr_t)d_workspace & 255) == 0, "workspace must be 256-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
-    unsigned char* ws = (unsigned char*)d_workspace;
-    float* x_cur = (float*)(ws + L.off_xa);
-    float* x_new = (float*)(ws + L.off_xb);
-    float* x_valid = (float*)(ws + L.off_valid);
-    float* d_metrics = (float*)(ws + L.off_metrics);
-    void* lm_ws = ws + L.off_lm;
-    const size_t lm_ws_bytes = L.total - L.off_lm;
-    const size_t row_bytes = (size_t)T * ndof * sizeof(float);
-
-#define CUDA_OK(expr)                                                                                        \
-    do {                                                                                                     \
-        cudaError_t e_ = (expr);                                                                             \
-        if (e_ != cudaSuccess) return fail(CPPFLOW_E_CUDA, "lm_alternating_loss: %s", cudaGetErrorString(e_)); \
-    } while (0)
-
-    CUDA_OK(cudaMemcpyAsync(x_cur, d_x_seed, row_bytes, cudaMemcpyDeviceToDevice, st));
-
-    // the reference starts with (pose_pos_valid, pose_rot_valid) = (True, False): the first step is pose-only (:219-220)
-    bool pose_pos_valid = true, pose_rot_valid = false, converged = false, has_valid = false;
-    int last_valid_idx = -1, n_tls = 0, i = 0;
-    double last_tl = 0.0;
-    int n_sched = 0;
-    const auto t0 = std::chrono::steady_clock::now();
-    for (i = 0; i < max_n_steps; ++i) {
-        bool was_differencing;
-        if (pose_pos_valid && pose_rot_valid) {
-            // virtual configs = the current iterate (:253): their residual is identically zero -> d_xv = NULL
-            if (int rc = cppflow_lm_full_step(robot, params_diff, x_cur, nullptr, d_target, 1, T, h_cuboids, h_Tcuboids,
-                                              n_obstacles, CPPFLOW_LM_CLAMP, lm_ws, lm_ws_bytes, x_new, stream))
-                return rc;
-            was_differencing = true;
-        } else {
-            if (int rc = cppflow_lm_pose_step(robot, params_pose, x_cur, d_target, T, T, 1, x_new, nullptr, nullptr, stream))
-                return rc;
-            was_differencing = false;
-        }
-        if (n_sched < CPPFLOW_LM_SCHEDULE_MAX - 1) result->schedule[n_sched++] = was_differencing ? 'd' : 'p';
-        float* tmp = x_cur; x_cur = x_new; x_new = tmp;  // clamp_to_joint_limits is fused into both steps (:259)
-
-        if (int rc = cppflow_path_metrics(robot, x_cur, d_target, 1, T, h_cuboids, h_Tcuboids, n_obstacles, d_metrics, stream))
-            return rc;
-        CUDA_OK(cudaMemcpyAsync(h_pinned_metrics, d_metrics, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
-        CUDA_OK(cudaStreamSynchronize(st));  // the one host round trip of the iteration
-        const float* m = h_pinned_metrics;   // max_pos_cm, max_rot_deg, mjac_deg, mjac_cm, tl, min_self, min_env
-        const double tl_new = m[4];
-        if (was_differencing) {
-            if (!converged && n_tls > 0) {
-                if (std::fabs(tl_new - last_tl) < convergence_threshold) {
-                    converged = true;
-                    if (last_valid_idx == i - 1) break;
-                }
-            }
-            last_tl = tl_new;
-            ++n_tls;
-        }
-        // x_is_valid (:836-923): strict '<' thresholds (evaluation_utils.py:29-75), then the collision check
-        pose_pos_valid = m[0] < constraints->max_allowed_position_error_cm;
-        pose_rot_valid = m[1] < constraints->max_allowed_rotation_error_deg;
-        const bool mjac_ok = m[2] < constraints->max_allowed_mjac_deg && m[3] < constraints->max_allowed_mjac_cm;
-        const bool is_valid = pose_pos_valid && pose_rot_valid && mjac_ok && !(m[5] < 0.f) && !(m[6] < 0.f);
-        if (is_valid) {
-            last_valid_idx = i;
-            has_valid = true;
-            CUDA_OK(cudaMemcpyAsync(x_valid, x_cur, row_bytes, cudaMemcpyDeviceToDevice, st));
-            if (converged) break;
-        }
-        const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        if (elapsed > tmax_sec) break;
-        if (has_valid) {
-            if (i > return_if_valid_after_n_steps) break;
-            if (i > max_n_steps) break;
-        }
-    }
-    if (i == max_n_steps && max_n_steps > 0) i = max_n_steps - 1;  // Python's loop variable after an exhausted range()
-    CUDA_OK(cudaMemcpyAsync(d_x_out, has_valid ? x_valid : x_cur, row_bytes, cudaMemcpyDeviceToDevice, st));
-    result->schedule[n_sched] = 0;
-    result->n_steps_taken = i;
-    result->is_valid = has_valid ? 1 : 0;
-    for (int k = 0; k < 8; ++k) result->last_metrics[k] = max_n_steps > 0 ? h_pinned_metrics[k] : 0.f;
-#undef CUDA_OK
-    return CPPFLOW_OK;
+    cppflow_lm_loop_job job;
+    job.robot = robot;
+    job.params_diff = params_diff;
+    job.params_pose = params_pose;
+    job.constraints = constraints;
+    job.d_x_seed = d_x_seed;
+    job.d_target = d_target;
+    job.T = T;
+    job.h_cuboids = h_cuboids;
+    job.h_Tcuboids = h_Tcuboids;
+    job.n_obstacles = n_obstacles;
+    job.max_n_steps = max_n_steps;
+    job.tmax_sec = tmax_sec;
+    job.return_if_valid_after_n_steps = return_if_valid_after_n_steps;
+    job.convergence_threshold = convergence_threshold;
+    job.d_workspace = d_workspace;
+    job.workspace_bytes = workspace_bytes;
+    job.h_pinned_metrics = h_pinned_metrics;
+    job.d_x_out = d_x_out;
+    job.result = result;
+    job.stream = stream;
+    return cppflow_lm_alternating_loss_many(1, &job);
 }

@@ -175,8 +175,9 @@ _WORKSPACES = {}
 
 
 def _workspace(device, nbytes: int, key: str) -> torch.Tensor:
-    """Grow-only scratch buffer per (device, purpose): the C ABI never allocates."""
-    k = (str(device), key)
+    """Grow-only scratch buffer per (device, current stream, purpose): the C ABI never allocates, and launches enqueued
+    on different streams (planners.plan_many runs one problem per stream) must not share scratch memory."""
+    k = (str(device), torch.cuda.current_stream(device).cuda_stream, key)
     buf = _WORKSPACES.get(k)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty((max(nbytes, 256),), device=device, dtype=torch.uint8)
@@ -273,9 +274,10 @@ def lm_alternating_loss(rid: int, ndof: int, params_diff: LmParamsC, params_pose
     dev = x_seed.device
     ws = _workspace(dev, lib.cppflow_lm_alternating_workspace_bytes(rid, T) + 256, "lm_loop")
     off = (-ws.data_ptr()) % 256
-    pinned = _PINNED.get(str(dev))
+    pkey = (str(dev), torch.cuda.current_stream(dev).cuda_stream)
+    pinned = _PINNED.get(pkey)
     if pinned is None:
-        pinned = _PINNED[str(dev)] = torch.empty(8, dtype=torch.float32).pin_memory()
+        pinned = _PINNED[pkey] = torch.empty(8, dtype=torch.float32).pin_memory()
     cons = _lib.ConstraintsC(constraints.max_allowed_position_error_cm, constraints.max_allowed_rotation_error_deg,
                              constraints.max_allowed_mjac_deg, constraints.max_allowed_mjac_cm)
     res = _lib.LmLoopResultC()
@@ -289,3 +291,63 @@ def lm_alternating_loss(rid: int, ndof: int, params_diff: LmParamsC, params_pose
         int(return_if_valid_after_n_steps), float(convergence_threshold), C.c_void_p(ws.data_ptr() + off),
         ws.numel() - off, C.c_void_p(pinned.data_ptr()), ptr(x_out), C.byref(res), stream_ptr(dev)))
     return x_out, int(res.n_steps_taken), bool(res.is_valid), res.schedule.decode(), list(res.last_metrics)
+
+
+def lm_alternating_loss_many(jobs):
+    """The alternating loop for several independent (problem, seed path) pairs in lock step (csrc/lm_loop.cu):
+    `jobs` = list of dicts with keys rid, ndof, params_diff, params_pose, constraints, x_seed [T, ndof], target [T, 7],
+    ob (Obstacles or None), max_n_steps, tmax_sec, return_if_valid_after_n_steps, convergence_threshold, stream
+    (torch.cuda.Stream).  -> list of (x_opt, n_steps_taken, is_valid, schedule, last_metrics)."""
+    import ctypes as C
+
+    lib = _lib.load()
+    n = len(jobs)
+    arr = (_lib.LmLoopJobC * n)()
+    keep, outs = [], []
+    for k, jb in enumerate(jobs):
+        x_seed = _check_q(jb["x_seed"], jb["ndof"], "x_seed")
+        T = x_seed.shape[0]
+        target = require_cuda(jb["target"], "target_path")
+        assert target.shape == (T, 7)
+        dev = x_seed.device
+        stream = jb["stream"]
+        nbytes = lib.cppflow_lm_alternating_workspace_bytes(jb["rid"], T) + 256
+        with torch.cuda.stream(stream):
+            ws = _workspace(dev, nbytes, "lm_loop")
+            x_out = torch.empty_like(x_seed)
+        off = (-ws.data_ptr()) % 256
+        pkey = (str(dev), stream.cuda_stream)
+        pinned = _PINNED.get(pkey)
+        if pinned is None:
+            pinned = _PINNED[pkey] = torch.empty(8, dtype=torch.float32).pin_memory()
+        c = jb["constraints"]
+        cons = _lib.ConstraintsC(c.max_allowed_position_error_cm, c.max_allowed_rotation_error_deg,
+                                 c.max_allowed_mjac_deg, c.max_allowed_mjac_cm)
+        res = _lib.LmLoopResultC()
+        cu, tc, no = _obs(jb["ob"])
+        tmax = jb["tmax_sec"]
+        a = arr[k]
+        a.robot = jb["rid"]
+        a.params_diff = C.pointer(jb["params_diff"])
+        a.params_pose = C.pointer(jb["params_pose"])
+        a.constraints = C.pointer(cons)
+        a.d_x_seed = x_seed.data_ptr()
+        a.d_target = target.data_ptr()
+        a.T = T
+        a.h_cuboids = C.cast(cu, _lib.c_float_p) if cu is not None else None
+        a.h_Tcuboids = C.cast(tc, _lib.c_float_p) if tc is not None else None
+        a.n_obstacles = no
+        a.max_n_steps = int(min(jb["max_n_steps"], 2 ** 31 - 1))
+        a.tmax_sec = 1e30 if tmax is None or tmax == float("inf") else float(tmax)
+        a.return_if_valid_after_n_steps = int(min(jb["return_if_valid_after_n_steps"], 2 ** 31 - 1))
+        a.convergence_threshold = float(jb["convergence_threshold"])
+        a.d_workspace = ws.data_ptr() + off
+        a.workspace_bytes = ws.numel() - off
+        a.h_pinned_metrics = pinned.data_ptr()
+        a.d_x_out = x_out.data_ptr()
+        a.result = C.pointer(res)
+        a.stream = stream.cuda_stream
+        keep.append((x_seed, target, ws, pinned, cons, cu, tc))
+        outs.append((x_out, res))
+    check(lib.cppflow_lm_alternating_loss_many(n, arr))
+    return [(x, int(r.n_steps_taken), bool(r.is_valid), r.schedule.decode(), list(r.last_metrics)) for x, r in outs]

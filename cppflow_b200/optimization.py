@@ -238,3 +238,21 @@ def run_lm_optimization(problem: Problem, x_seed: torch.Tensor, tmax_sec: float,
         convergence_threshold=convergence_threshold, save_images=False, results_df=results_df,
         mesh_validator=mesh_validator, native=native,
     )
+
+
+def run_lm_optimization_many(problems, x_seeds, streams, tmax_sec: float, max_n_steps: int,
+                             return_if_valid_after_n_steps: int, convergence_threshold: float):
+    """run_lm_optimization for several independent problems in lock step: problem i's kernels run on streams[i] and the
+    library takes every loop's decisions after having enqueued the next step of all of them.  Same results as one
+    run_lm_optimization call per problem.  -> list of OptimizationResult."""
+    jobs = []
+    for problem, x_seed, stream in zip(problems, x_seeds, streams):
+        robot = problem.robot
+        assert x_seed.shape == (problem.n_timesteps, robot.ndof)
+        jobs.append(dict(rid=robot.robot_id, ndof=robot.ndof, params_diff=ops.make_params(ALT_LOSS_V2_1_DIFF),
+                         params_pose=ops.make_params(ALT_LOSS_V2_1_POSE), constraints=problem.constraints, x_seed=x_seed,
+                         target=problem.target_path, ob=problem.obstacle_tables, max_n_steps=max_n_steps, tmax_sec=tmax_sec,
+                         return_if_valid_after_n_steps=return_if_valid_after_n_steps,
+                         convergence_threshold=convergence_threshold, stream=stream))
+    return [OptimizationResult(x_opt=x, n_steps_taken=n, is_valid=v, parallel_seed_idx=0, schedule=s)
+            for x, n, v, s, _ in ops.lm_alternating_loss_many(jobs)]

@@ -40,6 +40,7 @@ class LmIkCandidateGenerator:
         self.lambdas = self.LAMBDAS if n_steps is None else self.LAMBDAS[-n_steps:] if n_steps <= len(self.LAMBDAS) \
             else (self.LAMBDAS[0],) * (n_steps - len(self.LAMBDAS)) + self.LAMBDAS
         self.gen = torch.Generator().manual_seed(seed)
+        self._prm_cache = None
 
     def __call__(self, problem: Problem, k: int) -> torch.Tensor:
         robot, T = problem.robot, problem.n_timesteps
@@ -48,10 +49,15 @@ class LmIkCandidateGenerator:
         mid, half = lim.mean(dim=1), (lim[:, 1] - lim[:, 0]) / 2
         base = mid + 0.6 * half * (2 * torch.rand((k, 1, robot.ndof), generator=self.gen) - 1)
         x = base.expand(k, T, robot.ndof).reshape(k * T, robot.ndof).contiguous().to(dev)
-        for lam in self.lambdas:
-            prm = ops.make_params(replace(ALT_LOSS_V2_1_POSE, lm_lambda=lam))
-            x = ops.lm_pose_step(robot.robot_id, robot.ndof, prm, x, problem.target_path, True)
-        return x.reshape(k, T, robot.ndof)
+        bufs = (x, torch.empty_like(x))  # ping-pong: no allocation per step
+        for i, prm in enumerate(self._params()):
+            ops.lm_pose_step(robot.robot_id, robot.ndof, prm, bufs[i % 2], problem.target_path, True, out=bufs[(i + 1) % 2])
+        return bufs[len(self.lambdas) % 2].reshape(k, T, robot.ndof)
+
+    def _params(self):
+        if self._prm_cache is None:
+            self._prm_cache = [ops.make_params(replace(ALT_LOSS_V2_1_POSE, lm_lambda=lam)) for lam in self.lambdas]
+        return self._prm_cache
 
 
 def report_from_qpath(qpath: torch.Tensor, problem: Problem) -> PathReport:
@@ -169,20 +175,101 @@ class CppFlowPlanner(Planner):
                                          verbosity=self._cfg.verbosity)
         td.optimizer = time() - t0_opt
         debug_info["n_optimization_steps"] = result.n_steps_taken
-        x_opt = result.x_opt.detach()
-
         if result.is_valid:
-            if problem.initial_configuration is None:
-                return return_(x_opt)
+            return self._result_from_optimization(problem, result, td, debug_info, t0)
+        if self._cfg.do_rerun_if_optimization_fails and (rerun_data is None) and (not time_is_exceeded()):
+            kwargs["rerun_data"] = q_data
+            kwargs["t0"] = t0
+            return self.generate_plan(problem, **kwargs)
+        return return_(result.x_opt.detach())
+
+    def _result_from_optimization(self, problem: Problem, result, td: TimingData, debug_info: Dict, t0: float) -> PlannerResult:
+        """The plan returned after the LM loop (planners.py:426-452): the optimised path, with the requested initial
+        configuration swapped in when that keeps the plan valid."""
+
+        def return_(qpath):
+            return PlannerResult(report_from_qpath(qpath, problem),
+                                 TimingData(time() - t0, td.ikflow, td.coll_checking, td.batch_opt, td.dp_search, td.optimizer),
+                                 [], [], debug_info)
+
+        x_opt = result.x_opt.detach()
+        if result.is_valid and problem.initial_configuration is not None:
             init = problem.initial_configuration.to(x_opt.device)
             if torch.norm(init - x_opt[0]) < SUCCESS_THRESHOLD_initial_q_norm_dist:
                 return return_(x_opt)
             x_opt_swapped = torch.cat((init, x_opt[1:]), dim=0)
             if report_from_qpath(x_opt_swapped, problem).is_valid:
                 return return_(x_opt_swapped)
-            return return_(x_opt)
-        if self._cfg.do_rerun_if_optimization_fails and (rerun_data is None) and (not time_is_exceeded()):
-            kwargs["rerun_data"] = q_data
-            kwargs["t0"] = t0
-            return self.generate_plan(problem, **kwargs)
         return return_(x_opt)
+
+
+_STREAM_POOL: Dict[str, list] = {}
+
+
+def plan_many(planner_factory: Callable[[Problem], Planner], problems):
+    """Plan several independent problems in one batched run (BASELINE config 4: the 13 benchmark problems).
+
+    A single plan is a chain of small dependent launches with one host round trip per LM iteration (~1-3 ms at a few %
+    of the GPU).  Here every problem gets its own CUDA stream and scratch buffers and the stages run phase by phase:
+      1. candidates -> collision flags -> dp_search of every problem are enqueued without any host synchronisation;
+      2. one host read per problem for the reference's "< 95 % colliding" asserts (planners.py:237,247);
+      3. the alternating LM loops of all problems advance in lock step inside the library
+         (cppflow_lm_alternating_loss_many: the next step of every unfinished loop is enqueued before the host waits);
+      4. the plan reports.
+    Results equal those of one `generate_plan` call per problem.  Planners with a rerun option or
+    `return_only_1st_plan` set (and non-CppFlowPlanner planners) are run one after the other instead.
+    (Host threads do not help here: the stages are Python-bound and serialise on the GIL - 13 threads were 1.5x slower
+    than the sequential loop.)  -> list of PlannerResult in order."""
+    from .optimization import run_lm_optimization_many
+
+    problems = list(problems)
+    planners = [planner_factory(p) for p in problems]
+    if not problems:
+        return []
+    batchable = all(isinstance(pl, CppFlowPlanner) and not pl._cfg.return_only_1st_plan
+                    and not pl._cfg.do_rerun_if_large_dp_search_mjac and not pl._cfg.do_rerun_if_optimization_fails
+                    and pl._cfg.anytime_mode_enabled == planners[0]._cfg.anytime_mode_enabled for pl in planners)
+    if not batchable:
+        return [pl.generate_plan(p) for pl, p in zip(planners, problems)]
+    t0 = time()
+    device = problems[0].target_path.device
+    cur = torch.cuda.current_stream(device)
+    pool = _STREAM_POOL.setdefault(str(device), [])  # the same streams every call: their allocator pools and the
+    while len(pool) < len(problems):                   # per-stream scratch buffers (ops._workspace) are reused
+        pool.append(torch.cuda.Stream(device))
+    streams = pool[: len(problems)]
+    staged = []
+    for pl, p, s in zip(planners, problems, streams):
+        with torch.cuda.stream(s):
+            s.wait_stream(cur)
+            qs = pl._candidates(p, pl._cfg.k)
+            self_v, env_v = qpaths_batched_collisions(p, qs)
+            counts = torch.stack([self_v.sum(), env_v.sum()]).float()
+            if p.initial_configuration is not None:
+                qs[:, 0, :] = p.initial_configuration.to(qs.device)
+                self_v[:, 0] = False
+                env_v[:, 0] = False
+            search = dp_search(pl.robot, qs, self_v, env_v, verbosity=0).contiguous()
+            staged.append((qs, counts, search))
+    for p, s, (qs, counts, _) in zip(problems, streams, staged):
+        with torch.cuda.stream(s):
+            pct = counts.cpu() / (qs.shape[0] * p.n_timesteps) * 100
+        assert pct[0] < 95.0, f"too many self collisions: {pct[0]} %"
+        assert pct[1] < 95.0, f"too many env collisions: {pct[1]} %"
+    t_search = time() - t0
+    cfg = planners[0]._cfg
+    tmax = min(pl._cfg.tmax_sec for pl in planners) - (time() - t0)
+    t0_opt = time()
+    if cfg.anytime_mode_enabled:
+        results = run_lm_optimization_many(problems, [st[2] for st in staged], streams, tmax, 75, int(1e8),
+                                           OPTIMIZATION_CONVERGENCE_THRESHOLD)
+    else:
+        results = run_lm_optimization_many(problems, [st[2] for st in staged], streams, tmax, 20, 0, 1e6)
+    t_opt = time() - t0_opt
+    out = []
+    for pl, p, s, res in zip(planners, problems, streams, results):
+        with torch.cuda.stream(s):
+            td = TimingData(-1, 0.0, t_search, 0.0, 0.0, t_opt)
+            out.append(pl._result_from_optimization(p, res, td, {"n_optimization_steps": res.n_steps_taken}, t0))
+        cur.wait_stream(s)
+    return out

@@ -177,6 +177,34 @@ int cppflow_lm_alternating_loss(int robot, const cppflow_lm_params* params_diff,
                                 double convergence_threshold, void* d_workspace, size_t workspace_bytes,
                                 float* h_pinned_metrics, float* d_x_out, cppflow_lm_loop_result* result, void* stream);
 
+/* The same loop for several independent paths / problems at once (BASELINE config 4: the 13 benchmark problems in one
+ * run).  One job per path, each with its own stream, workspace and pinned metrics buffer; the next step of EVERY
+ * unfinished job is enqueued before the host waits for any of them, so the jobs overlap on the device while the host
+ * takes each job's decisions exactly as cppflow_lm_alternating_loss does (which is this call with one job). */
+typedef struct cppflow_lm_loop_job {
+    int32_t robot;
+    const cppflow_lm_params* params_diff;
+    const cppflow_lm_params* params_pose;
+    const cppflow_constraints* constraints;
+    const float* d_x_seed; /* [T, ndof] */
+    const float* d_target; /* [T, 7] */
+    int64_t T;
+    const float* h_cuboids;
+    const float* h_Tcuboids;
+    int32_t n_obstacles;
+    int32_t max_n_steps;
+    double tmax_sec;
+    int32_t return_if_valid_after_n_steps;
+    double convergence_threshold;
+    void* d_workspace;
+    size_t workspace_bytes;
+    float* h_pinned_metrics; /* 8 floats, page-locked */
+    float* d_x_out;          /* [T, ndof] */
+    cppflow_lm_loop_result* result;
+    void* stream;
+} cppflow_lm_loop_job;
+int cppflow_lm_alternating_loss_many(int n_jobs, const cppflow_lm_loop_job* jobs);
+
 /* joint_limit_almost_violations_3d(robot, qs, eps_revolute, eps_prismatic) -> float32 0/1 [n]  (search.py:25-52) */
 int cppflow_joint_limit_flags(int robot, const float* d_q, int64_t n, float eps_revolute, float eps_prismatic,
                               float* d_flags, void* stream);

@@ -173,3 +173,26 @@ def test_path_metrics_cluster_split_matches_single_cta():
         one = ops.path_metrics(rob.robot_id, rob.ndof, qs[p].contiguous(), problem.target_path, 1, T, problem.obstacle_tables)
         assert torch.equal(one[0, [0, 1, 2, 3, 5, 6]], many[p, [0, 1, 2, 3, 5, 6]]), p
         assert abs(float(one[0, 4]) - float(many[p, 4])) <= 1e-5 * float(many[p, 4]), p
+
+
+def test_config4_plan_many_concurrent_equals_sequential():
+    """BASELINE config 4 in ONE run: the 13 problems planned in one batched run (one CUDA stream each, lock-step LM loops,
+    per-stream scratch buffers) give exactly the plans of 13 sequential runs."""
+    from cppflow_b200.data_type_utils import ALL_PROBLEM_FILENAMES
+    from cppflow_b200.data_types import PlannerSettings
+    from cppflow_b200.planners import CppFlowPlanner, LmIkCandidateGenerator, plan_many
+
+    problems = [_problem(name) for name in ALL_PROBLEM_FILENAMES]
+
+    def factory(problem):
+        return CppFlowPlanner(PlannerSettings(k=175, tmax_sec=30.0, anytime_mode_enabled=False, verbosity=0),
+                              problem.robot, LmIkCandidateGenerator(seed=1))
+
+    seq = [factory(p).generate_plan(p) for p in problems]
+    for _ in range(2):
+        con = plan_many(factory, problems)
+        assert len(con) == len(seq)
+        for name, a, b in zip(ALL_PROBLEM_FILENAMES, seq, con):
+            assert a.plan.is_valid == b.plan.is_valid, name
+            assert torch.equal(a.plan.q_path, b.plan.q_path), name
+            assert a.debug_info.get("n_optimization_steps") == b.debug_info.get("n_optimization_steps"), name
