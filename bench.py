@@ -208,7 +208,7 @@ def plan_latency_gpu(dev, k=175, reps=10):
 
 def plan_all_problems_gpu(dev, k=175, reps=5):
     """BASELINE config 4: the 13 benchmark problems (candidate generation included), one after the other and
-    concurrently (planners.plan_many: one CUDA stream per problem, stages phase by phase, LM loops in lock step).  Host wall clock, median."""
+    in one batched run (planners.plan_many: one CUDA stream per problem, stages phase by phase, LM loops in lock step).  Host wall clock, median."""
     from cppflow_b200.data_type_utils import ALL_PROBLEM_FILENAMES, problem_from_filename
     from cppflow_b200.data_types import PlannerSettings
     from cppflow_b200.planners import CppFlowPlanner, LmIkCandidateGenerator, plan_many
@@ -226,7 +226,7 @@ def plan_all_problems_gpu(dev, k=175, reps=5):
         return plan_many(factory, problems)
 
     out = {}
-    for name, fn in (("sequential_ms", sequential), ("batched_ms", concurrent)):
+    for name, fn in (("sequential_ms", sequential), ("batched_ms", batched)):
         fn()
         torch.cuda.synchronize(dev)
         ts = []
