@@ -99,6 +99,22 @@ class HostPipeline:
         return out_host
 
 
+def split_paths(n_paths: int, n_chunks: int):
+    """Contiguous chunks [(first path, count), ...] covering n_paths: multiples of 256 paths (the assembly CTA) when
+    there are enough paths, of 16 (the solve's path group) otherwise; no empty chunks."""
+    gran = 256 if n_paths >= 256 * n_chunks else 16 if n_paths >= 16 * n_chunks else 1
+    units = (n_paths + gran - 1) // gran
+    n_chunks = max(1, min(n_chunks, units))
+    base, rem = divmod(units, n_chunks)
+    chunks, start = [], 0
+    for c in range(n_chunks):
+        n = min((base + (1 if c < rem else 0)) * gran, n_paths - start)
+        if n > 0:
+            chunks.append((start, n))
+        start += n
+    return chunks
+
+
 class ResidentPipeline:
     """LM iterations over device-resident paths with the two kernels of the step overlapped across path chunks.
 
@@ -120,17 +136,7 @@ class ResidentPipeline:
         self.device = problem.target_path.device if device is None else torch.device(device)
         self.prm = ops.make_params(params if params is not None else all_terms_parameters())
         self.overlap = overlap
-        gran = 256 if n_paths >= 256 * n_chunks else 16 if n_paths >= 16 * n_chunks else 1
-        units = (n_paths + gran - 1) // gran
-        n_chunks = max(1, min(n_chunks, units))
-        base, rem = divmod(units, n_chunks)
-        self.chunks = []
-        start = 0
-        for c in range(n_chunks):
-            n = min((base + (1 if c < rem else 0)) * gran, n_paths - start)
-            if n > 0:
-                self.chunks.append((start, n))
-            start += n
+        self.chunks = split_paths(n_paths, n_chunks)
         self.streams = [torch.cuda.Stream(self.device) for _ in self.chunks]
         lib = ops._lib.load()
         self.ws = [torch.empty((lib.cppflow_lm_full_workspace_bytes(self.robot.robot_id, n, self.T),), device=self.device,

@@ -340,11 +340,20 @@ def test_full_step_full_size_path_independence(robots):
     assert torch.equal(step(x0[sl].contiguous(), 1), ref[sl])
 
     seq = x0
-    for _ in range(3):
+    for it in range(3):
         seq = step(seq, P)
+        if it == 1:
+            seq2 = seq
     for n_chunks in (1, 3, 4):
         pipe = ResidentPipeline(problem, P, all_terms_parameters(), n_chunks=n_chunks)
         assert torch.equal(pipe.iterate(x0, 3), seq), n_chunks
+    # ragged sizes: path counts that fill neither the 256-path assembly CTAs nor the 16-path solve groups
+    for n_paths, n_chunks in ((1000, 3), (37, 4)):
+        xs = x0[: n_paths * T].contiguous()
+        one = step(step(xs, n_paths), n_paths)
+        assert torch.equal(one, seq2[: n_paths * T]), (n_paths, n_chunks)
+        pipe = ResidentPipeline(problem, n_paths, all_terms_parameters(), n_chunks=n_chunks)
+        assert torch.equal(pipe.iterate(xs, 2), one), (n_paths, n_chunks)
     # and the full-size iterations descend: the mean over paths of the maximum position error shrinks
     m0 = ops.path_metrics(rob.robot_id, D, x0, problem.target_path, P, T, ob)
     m1 = ops.path_metrics(rob.robot_id, D, seq, problem.target_path, P, T, ob)

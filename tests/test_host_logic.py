@@ -160,3 +160,19 @@ def test_gather_argmin_two_ranks_gloo():
     metrics[:, 5:7] = 0.1
     metrics[5, 4] = metrics[29, 4] = 0.5
     assert gather_costs_and_argmin(metrics, DEFAULT_CONSTRAINTS, 0, 1) == (pytest.approx(0.5), 0, 5)
+
+
+def test_split_paths_covers_every_path_once():
+    """pipeline.split_paths: contiguous chunks, multiples of the assembly CTA (256 paths) / the solve group (16) when
+    the path count allows, no empty chunk, every path in exactly one chunk."""
+    from cppflow_b200.pipeline import split_paths
+
+    for n, c in [(8192, 4), (8192, 3), (8192, 1), (1000, 3), (300, 4), (17, 4), (5, 8), (1, 4), (4096, 16), (257, 2)]:
+        chunks = split_paths(n, c)
+        assert 1 <= len(chunks) <= c
+        assert chunks[0][0] == 0 and sum(k for _, k in chunks) == n
+        for (a, ka), (b, _) in zip(chunks, chunks[1:]):
+            assert a + ka == b and ka > 0
+        gran = 256 if n >= 256 * c else 16 if n >= 16 * c else 1
+        assert all(k % gran == 0 for _, k in chunks[:-1])
+    assert split_paths(8192, 4) == [(0, 2048), (2048, 2048), (4096, 2048), (6144, 2048)]
