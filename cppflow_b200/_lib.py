@@ -114,6 +114,7 @@ _PROTOTYPES = {
     "cppflow_jacobian": (_I, [_I, _VP, _I64, _VP, _VP]),
     "cppflow_pose_errors": (_I, [_I, _VP, _VP, _I64, _I64, _VP, _VP, _VP]),
     "cppflow_lm_pose_step": (_I, [_I, C.POINTER(LmParamsC), _VP, _VP, _I64, _I64, _I, _VP, _VP, _VP, _VP]),
+    "cppflow_lm_pose_steps": (_I, [_I, C.POINTER(LmParamsC), c_float_p, _I, _VP, _VP, _VP, _I64, _I64, _I, _VP]),
     "cppflow_clamp_to_joint_limits": (_I, [_I, _VP, _I64, _VP]),
     "cppflow_self_collision_distances": (_I, [_I, _VP, _I64, _VP, _VP, _VP]),
     "cppflow_env_collision_distances": (_I, [_I, _VP, _I64, c_float_p, c_float_p, _VP, _VP, _VP]),

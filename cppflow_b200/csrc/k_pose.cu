@@ -278,6 +278,15 @@ extern "C" int cppflow_pose_errors(int robot, const float* d_q, const float* d_t
     return CPPFLOW_OK;
 }
 
+static int robot_dof(int robot) {
+    switch (robot) {
+        case ROBOT_FETCH: return Fetch::NDOF;
+        case ROBOT_FETCH_ARM: return FetchArm::NDOF;
+        case ROBOT_PANDA: return Panda::NDOF;
+        default: return 0;
+    }
+}
+
 extern "C" int cppflow_lm_pose_step(int robot, const cppflow_lm_params* p, const float* d_q, const float* d_target,
                                     int64_t n, int64_t n_targets, int do_clamp, float* d_x_out, float* d_J_out,
                                     float* d_e_out, void* stream) {
@@ -290,6 +299,28 @@ extern "C" int cppflow_lm_pose_step(int robot, const cppflow_lm_params* p, const
                                       d_q, d_target, n, n_targets, p->alpha_position, p->alpha_rotation, p->lm_lambda,
                                       do_clamp, d_x_out, d_J_out, d_e_out));
     CPPFLOW_CHECK_LAUNCH();
+    return CPPFLOW_OK;
+}
+
+extern "C" int cppflow_lm_pose_steps(int robot, const cppflow_lm_params* p, const float* h_lambdas, int n_steps,
+                                     float* d_q, float* d_tmp, const float* d_target, int64_t n, int64_t n_targets,
+                                     int do_clamp, void* stream) {
+    CPPFLOW_CHECK_ARG(p != nullptr && n >= 0 && n_steps >= 0, "params, n, n_steps");
+    if (n == 0 || n_steps == 0) return CPPFLOW_OK;
+    CPPFLOW_CHECK_ARG(d_q && d_tmp && d_target && h_lambdas && n_targets > 0, "null pointer");
+    float* bufs[2] = {d_q, d_tmp};
+    for (int i = 0; i < n_steps; ++i) {
+        const float lam = h_lambdas[i];
+        CPPFLOW_DISPATCH_ROBOT(robot, lm_pose_step_kernel<M><<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(
+                                          bufs[i & 1], d_target, n, n_targets, p->alpha_position, p->alpha_rotation, lam,
+                                          do_clamp, bufs[(i + 1) & 1], nullptr, nullptr));
+    }
+    CPPFLOW_CHECK_LAUNCH();
+    if (n_steps & 1) {  // the result sits in d_tmp: bring it home
+        cudaError_t e = cudaMemcpyAsync(d_q, d_tmp, (size_t)n * robot_dof(robot) * sizeof(float), cudaMemcpyDeviceToDevice,
+                                        (cudaStream_t)stream);
+        if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "lm_pose_steps: %s", cudaGetErrorString(e));
+    }
     return CPPFLOW_OK;
 }
 

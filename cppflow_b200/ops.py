@@ -133,6 +133,19 @@ def lm_pose_step(rid: int, ndof: int, params: LmParamsC, q: torch.Tensor, target
     return x_out
 
 
+def lm_pose_steps_(rid: int, ndof: int, params: LmParamsC, lambdas, q: torch.Tensor, target: torch.Tensor,
+                   clamp: bool = True) -> torch.Tensor:
+    """len(lambdas) pose-only LM steps in place on q (step i with damping lambdas[i]): one library call."""
+    assert q.is_cuda and q.dtype == torch.float32 and q.is_contiguous() and q.dim() == 2 and q.shape[1] == ndof
+    target = require_cuda(target, "target_path")
+    assert target.dim() == 2 and target.shape[1] == 7 and q.shape[0] % target.shape[0] == 0
+    tmp = torch.empty_like(q)
+    lam = _lib.host_floats([float(v) for v in lambdas])
+    check(_lib.load().cppflow_lm_pose_steps(rid, params, lam, len(lambdas), ptr(q), ptr(tmp), ptr(target), q.shape[0],
+                                            target.shape[0], int(clamp), stream_ptr(q.device)))
+    return q
+
+
 def clamp_to_joint_limits_(rid: int, ndof: int, q: torch.Tensor) -> torch.Tensor:
     assert q.is_cuda and q.dtype == torch.float32 and q.is_contiguous(), "in-place clamp needs a contiguous fp32 CUDA tensor"
     assert q.dim() == 2 and q.shape[1] == ndof

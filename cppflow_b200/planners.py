@@ -5,7 +5,6 @@ IKFlow (the conditional normalising flow that proposes the k candidate joint pat
 scope - its pretrained weights are not available offline - so the candidate generator is a pluggable callable
 `(problem, k) -> [k, T, ndof]`.  The default, `LmIkCandidateGenerator`, draws k smooth random joint paths and pulls
 each waypoint onto the target pose with a few pose-only LM steps of the CUDA kernel."""
-from dataclasses import replace
 from time import time
 from typing import Callable, Dict, Optional, Tuple
 
@@ -40,7 +39,7 @@ class LmIkCandidateGenerator:
         self.lambdas = self.LAMBDAS if n_steps is None else self.LAMBDAS[-n_steps:] if n_steps <= len(self.LAMBDAS) \
             else (self.LAMBDAS[0],) * (n_steps - len(self.LAMBDAS)) + self.LAMBDAS
         self.gen = torch.Generator().manual_seed(seed)
-        self._prm_cache = None
+        self._prm = ops.make_params(ALT_LOSS_V2_1_POSE)
 
     def __call__(self, problem: Problem, k: int) -> torch.Tensor:
         robot, T = problem.robot, problem.n_timesteps
@@ -49,15 +48,8 @@ class LmIkCandidateGenerator:
         mid, half = lim.mean(dim=1), (lim[:, 1] - lim[:, 0]) / 2
         base = mid + 0.6 * half * (2 * torch.rand((k, 1, robot.ndof), generator=self.gen) - 1)
         x = base.expand(k, T, robot.ndof).reshape(k * T, robot.ndof).contiguous().to(dev)
-        bufs = (x, torch.empty_like(x))  # ping-pong: no allocation per step
-        for i, prm in enumerate(self._params()):
-            ops.lm_pose_step(robot.robot_id, robot.ndof, prm, bufs[i % 2], problem.target_path, True, out=bufs[(i + 1) % 2])
-        return bufs[len(self.lambdas) % 2].reshape(k, T, robot.ndof)
-
-    def _params(self):
-        if self._prm_cache is None:
-            self._prm_cache = [ops.make_params(replace(ALT_LOSS_V2_1_POSE, lm_lambda=lam)) for lam in self.lambdas]
-        return self._prm_cache
+        ops.lm_pose_steps_(robot.robot_id, robot.ndof, self._prm, self.lambdas, x, problem.target_path, True)
+        return x.reshape(k, T, robot.ndof)
 
 
 def report_from_qpath(qpath: torch.Tensor, problem: Problem) -> PathReport:

@@ -100,6 +100,13 @@ int cppflow_lm_pose_step(int robot, const cppflow_lm_params* params, const float
                          int64_t n, int64_t n_targets, int do_clamp, float* d_x_out, float* d_J_out, float* d_e_out,
                          void* stream);
 
+/* n_steps pose-only LM steps in a row, step i with damping h_lambdas[i] (host array) instead of params->lm_lambda, in
+ * place on d_q [n, ndof] with d_tmp [n, ndof] as the second buffer.  No reference counterpart as a single call: it is
+ * levenberg_marquardt_only_pose applied repeatedly, which the stand-in candidate generator (planners.py) uses to pull
+ * random joint configurations onto the target poses. */
+int cppflow_lm_pose_steps(int robot, const cppflow_lm_params* params, const float* h_lambdas, int n_steps, float* d_q,
+                          float* d_tmp, const float* d_target, int64_t n, int64_t n_targets, int do_clamp, void* stream);
+
 /* clamp_to_joint_limits(robot, x), in place   (optimization_utils.py:823-833) */
 int cppflow_clamp_to_joint_limits(int robot, float* d_q, int64_t n, void* stream);
 

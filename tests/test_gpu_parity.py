@@ -358,3 +358,24 @@ def test_full_step_full_size_path_independence(robots):
     m0 = ops.path_metrics(rob.robot_id, D, x0, problem.target_path, P, T, ob)
     m1 = ops.path_metrics(rob.robot_id, D, seq, problem.target_path, P, T, ob)
     assert float(m1[:, 0].mean()) < float(m0[:, 0].mean()), (m0[:, 0].mean(), m1[:, 0].mean(), m0[:, 0].max(), m1[:, 0].max())
+
+
+@pytest.mark.parametrize("r", ROBOTS)
+@pytest.mark.parametrize("n_steps", [1, 4, 5])
+def test_pose_steps_equal_repeated_pose_step(robots, r, n_steps):
+    """cppflow_lm_pose_steps (n damped pose-only steps in one call, in place) == n calls of cppflow_lm_pose_step."""
+    from dataclasses import replace
+
+    from cppflow_b200 import ops
+    from cppflow_b200.lm_hyper_parameters import ALT_LOSS_V2_1_POSE
+
+    rob = robots[r]
+    m, target, x0 = synthetic_problem(r, 7, 33, seed=5, noise=0.3)
+    lambdas = [1e-1, 1e-2, 1e-3, 1e-5, 1e-6][:n_steps]
+    x = x0.to(DEV)
+    for lam in lambdas:
+        x = ops.lm_pose_step(rob.robot_id, rob.ndof, ops.make_params(replace(ALT_LOSS_V2_1_POSE, lm_lambda=lam)), x,
+                             target.to(DEV), True)
+    y = x0.to(DEV).clone()
+    ops.lm_pose_steps_(rob.robot_id, rob.ndof, ops.make_params(ALT_LOSS_V2_1_POSE), lambdas, y, target.to(DEV), True)
+    assert torch.equal(x, y)
