@@ -81,3 +81,33 @@ def test_no_cpu_fallback():
         rob.forward_kinematics(torch.zeros((3, 7)))
     with pytest.raises(NotImplementedError):
         rob.config_self_collides(None)
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """sizeof / offsetof of every struct of include/cppflow_b200.h, as gcc sees them, against the ctypes mirrors."""
+    import shutil
+    import subprocess
+
+    from cppflow_b200 import _lib
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "sizes.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "cppflow_b200.h"\n'
+        "int main(void) {\n"
+        '  printf("%zu %zu %zu %zu %zu\\n", sizeof(cppflow_lm_params), sizeof(cppflow_robot_info), sizeof(cppflow_constraints),\n'
+        "         sizeof(cppflow_lm_loop_result), sizeof(cppflow_lm_loop_job));\n"
+        '  printf("%zu %zu %zu %zu %zu\\n", offsetof(cppflow_lm_loop_job, T), offsetof(cppflow_lm_loop_job, tmax_sec),\n'
+        "         offsetof(cppflow_lm_loop_job, convergence_threshold), offsetof(cppflow_lm_loop_job, result),\n"
+        "         offsetof(cppflow_lm_loop_result, schedule));\n"
+        "  return 0;\n}\n")
+    exe = tmp_path / "sizes"
+    subprocess.run([gcc, "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    sizes = [int(v) for v in out]
+    J, R_ = _lib.LmLoopJobC, _lib.LmLoopResultC
+    assert sizes == [ctypes.sizeof(_lib.LmParamsC), ctypes.sizeof(_lib.RobotInfoC), ctypes.sizeof(_lib.ConstraintsC),
+                     ctypes.sizeof(R_), ctypes.sizeof(J), J.T.offset, J.tmax_sec.offset, J.convergence_threshold.offset,
+                     J.result.offset, R_.schedule.offset]
