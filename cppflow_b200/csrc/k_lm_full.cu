@@ -638,6 +638,163 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
     cp_async_wait<0>();
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// The same solve for a HANDFUL of paths (the alternating LM loop refines one path per call and waits for the answer).
+// There the streaming kernel is pure latency: one warp walks a chain of T/2 steps and every step pays the TMA issue,
+// the mbarrier wait, the ring bookkeeping and a global store on top of the 8x8 sweep (~1.4 us per step, 0.2 ms for
+// T = 295).  A path's blocks are only T x 176 bytes: this kernel gathers them (and the path's q rows) into shared
+// memory once with cp.async, then eliminates, factorises the middle block and back-substitutes entirely out of
+// shared memory, results overwriting the blocks in place.  One single-warp CTA per path; every lane pair (2k, 2k+1)
+// runs the two sides redundantly (same addresses, same values), so the warp never diverges and the shuffles of the
+// middle block are the streaming kernel's.  The arithmetic and its order are identical: results are bit-identical.
+template <class M>
+__global__ void __launch_bounds__(32)
+lm_block_solve_resident_kernel(const float* __restrict__ q, int64_t P, int64_t T, const SolveParams prm,
+                               const float* __restrict__ ws, float* __restrict__ x_out) {
+    constexpr int D = M::NDOF;
+    constexpr int NT = BlockLayout<D>::NT;
+    constexpr int NW = BlockLayout<D>::NW;
+    constexpr int NV = NW / 4;
+    constexpr int DQ = (D + 3) / 4 * 4;  // q row padded to float4
+    constexpr int BLK_BYTES = NV * 16 * 16;
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    float4* blk_s = reinterpret_cast<float4*>(smem_all);                 // [T][NV]
+    float* q_s = reinterpret_cast<float*>(smem_all + (size_t)T * NV * 16);  // [T][DQ]
+    const int lane = threadIdx.x;
+    const int64_t p = blockIdx.x;
+    const int64_t g = p >> 4;
+    const int l = (int)(p & 15);
+    const unsigned char* wsg = reinterpret_cast<const unsigned char*>(ws) + g * T * BLK_BYTES;
+    const float* qp = q + p * T * D;
+    for (int64_t idx = lane; idx < T * NV; idx += 32) {
+        const int64_t t = idx / NV;
+        const int k = (int)(idx - t * NV);
+        cp_async16(blk_s + idx, wsg + t * BLK_BYTES + ((size_t)k * 16 + l) * 16);
+    }
+    for (int64_t idx = lane; idx < T * D; idx += 32) {
+        const int64_t t = idx / D;
+        cp_async4(q_s + t * DQ + (idx - t * D), qp + idx);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+
+    const int side = lane & 1;
+    const int64_t m = T / 2;
+    const int64_t n0 = m, n1 = T - 1 - m;
+    const int64_t n_side = side == 0 ? n0 : n1;
+    const int64_t n_iter = n0 > n1 ? n0 : n1;
+    const BetaSel<M> bs(prm.b_rev, prm.b_pri);
+    auto t_of = [&](int64_t k) { return side == 0 ? k : T - 1 - k; };
+    auto read_block = [&](int64_t t, float (&v)[NW]) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const float4 f = blk_s[t * NV + k];
+            v[4 * k] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w;
+        }
+    };
+    auto store_x = [&](int64_t t, float (&xn)[D]) {
+        if (prm.do_clamp) {
+            static_for<D>([&](auto Dd) {
+                constexpr int d = decltype(Dd)::value;
+                xn[d] = fminf(fmaxf(xn[d], dof_lower<M>(d)), dof_upper<M>(d));
+            });
+        }
+        if (lane < 2) {
+            float* xo = x_out + (p * T + t) * D;
+#pragma unroll
+            for (int d = 0; d < D; ++d) xo[d] = xn[d];
+        }
+    };
+
+    float nS[NT], u[D];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) nS[k] = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) u[d] = 0.f;
+    for (int64_t k = 0; k < n_side; ++k) {
+        const int64_t t = t_of(k);
+        float blk[NW];
+        read_block(t, blk);
+        static_for<D>([&](auto Ii) {
+            constexpr int i = decltype(Ii)::value;
+            u[i] = fmaf(bs.template b<i>(), u[i], blk[NT + i]);
+            static_for<i + 1>([&](auto Jj) {
+                constexpr int j = decltype(Jj)::value;
+                nS[tri(i, j)] = fmaf(bs.template bb<i, j>(), nS[tri(i, j)], blk[tri(i, j)]);
+            });
+        });
+        sweep_neg_inverse<D>(nS, u);
+        float v[NW];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) v[i] = nS[i];
+#pragma unroll
+        for (int d = 0; d < D; ++d) v[NT + d] = u[d];
+#pragma unroll
+        for (int i = NT + D; i < NW; ++i) v[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) blk_s[t * NV + i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+    __syncwarp();
+
+    float dx[D];
+    {
+        float Sm[NT];
+        float blk[NW];
+        read_block(m, blk);
+        static_for<D>([&](auto Ii) {
+            constexpr int i = decltype(Ii)::value;
+            const float uo = __shfl_xor_sync(0xffffffffu, u[i], 1);
+            dx[i] = fmaf(bs.template b<i>(), u[i] + uo, blk[NT + i]);
+            static_for<i + 1>([&](auto Jj) {
+                constexpr int j = decltype(Jj)::value;
+                const float so = __shfl_xor_sync(0xffffffffu, nS[tri(i, j)], 1);
+                Sm[tri(i, j)] = fmaf(bs.template bb<i, j>(), nS[tri(i, j)] + so, blk[tri(i, j)]);
+            });
+        });
+        sweep_neg_inverse<D>(Sm, dx);
+        if (side == 0) {
+            float xn[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) xn[i] = q_s[m * DQ + i] + dx[i];
+            store_x(m, xn);
+        }
+    }
+
+    for (int64_t k = n_side - 1; k >= 0; --k) {
+        const int64_t t = t_of(k);
+        float blk[NW], xn[D];
+        read_block(t, blk);
+#pragma unroll
+        for (int d = 0; d < D; ++d) xn[d] = q_s[t * DQ + d];
+        float z[D];
+        static_for<D>([&](auto Ii) {
+            constexpr int i = decltype(Ii)::value;
+            z[i] = bs.template b<i>() * dx[i];
+        });
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            float a0 = blk[NT + i], a1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < D; j += 2) {
+                a0 = fmaf(-(j <= i ? blk[tri(i, j)] : blk[tri(j, i)]), z[j], a0);
+                if (j + 1 < D) a1 = fmaf(-(j + 1 <= i ? blk[tri(i, j + 1)] : blk[tri(j + 1, i)]), z[j + 1], a1);
+            }
+            dx[i] = a0 + a1;
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) xn[i] += dx[i];
+        store_x(t, xn);
+    }
+}
+
+constexpr int64_t SOLVE_RESIDENT_MAX_PATHS = 8;  // beyond a handful of paths the streaming kernel's throughput wins
+
+template <class M>
+static size_t solve_resident_smem(int64_t T) {
+    return (size_t)T * (BlockLayout<M::NDOF>::NW * 4 + (M::NDOF + 3) / 4 * 16);
+}
+
 template <class M>
 static void make_params(const cppflow_lm_params* p, int n_obstacles, int do_clamp, AssembleParams& ap, SolveParams& sp) {
     ap = AssembleParams{};
@@ -719,6 +876,17 @@ static int launch_solve(const cppflow_lm_params* p, const float* q, int64_t P, i
     AssembleParams ap;
     SolveParams sp;
     make_params<M>(p, 0, flags & CPPFLOW_LM_CLAMP, ap, sp);
+    if (P <= SOLVE_RESIDENT_MAX_PATHS && solve_resident_smem<M>(T) <= 200 * 1024) {
+        const size_t sh = solve_resident_smem<M>(T);
+        static size_t attr_bytes = 0;  // per template instantiation
+        if (sh > attr_bytes) {
+            cudaError_t e = cudaFuncSetAttribute(lm_block_solve_resident_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            attr_bytes = 200 * 1024;
+        }
+        lm_block_solve_resident_kernel<M><<<(unsigned)P, 32, sh, st>>>(q, P, T, sp, ws, x_out);
+        return CPPFLOW_OK;
+    }
     if (flags & CPPFLOW_LM_OVERLAP) return launch_solve_variant<M, SOLVE_RING_OVERLAP>(sp, q, P, T, true, ws, x_out, st);
     return launch_solve_variant<M, SOLVE_RING_ALONE>(sp, q, P, T, false, ws, x_out, st);
 }

@@ -379,3 +379,32 @@ def test_pose_steps_equal_repeated_pose_step(robots, r, n_steps):
     y = x0.to(DEV).clone()
     ops.lm_pose_steps_(rob.robot_id, rob.ndof, ops.make_params(ALT_LOSS_V2_1_POSE), lambdas, y, target.to(DEV), True)
     assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("r", ROBOTS)
+@pytest.mark.parametrize("T", [1, 2, 3, 4, 10, 33, 300])
+def test_resident_solve_equals_streaming_solve(robots, r, T):
+    """Up to 8 paths the block solve runs out of shared memory (lm_block_solve_resident_kernel), beyond that it streams
+    the blocks with TMA: same arithmetic in the same order, so a path's result is bit-identical whichever kernel it
+    went through - for the shortest paths too (no elimination step at T = 1, one side only at T = 2)."""
+    from dataclasses import replace
+
+    from cppflow_b200 import ops
+    from cppflow_b200.lm_hyper_parameters import all_terms_parameters
+
+    rob = robots[r]
+    P = 24
+    m, target, x0 = synthetic_problem(r, P, T, seed=31)
+    cuboids, Tcuboids = cuboid_tensors(OBSTACLES[r])
+    pms = all_terms_parameters() if T > 8 else replace(all_terms_parameters(), use_virtual_configs=False)
+    prm, ob, x0, target = ops.make_params(pms), ops.Obstacles(cuboids, Tcuboids), x0.to(DEV), target.to(DEV)
+
+    def step(x, n):
+        return ops.lm_full_step(rob.robot_id, rob.ndof, prm, x, None, target, n, T, ob, True)
+
+    streaming = step(x0, P)  # 24 paths: the TMA kernel
+    assert torch.isfinite(streaming).all()
+    for p in (0, 5, 23):
+        assert torch.equal(step(x0[p * T:(p + 1) * T].contiguous(), 1), streaming[p * T:(p + 1) * T]), p
+    assert torch.equal(step(x0[8 * T:16 * T].contiguous(), 8), streaming[8 * T:16 * T])
+    assert torch.equal(step(x0[:3 * T].contiguous(), 3), streaming[:3 * T])
