@@ -268,14 +268,12 @@ dp_sweep_cluster_kernel(const float* __restrict__ q, const float* __restrict__ e
                         if (val < best) { best = val; bj = j; }
                     }
                 }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const float ov = __shfl_down_sync(0xffffffffu, best, off);
-                    const int oj = __shfl_down_sync(0xffffffffu, bj, off);
-                    if (ov < best || (ov == best && oj < bj)) { best = ov; bj = oj; }
-                }
-                best = __shfl_sync(0xffffffffu, best, 0);
-                bj = __shfl_sync(0xffffffffu, bj, 0);
+                // lexicographic (value, index) minimum over the warp with two REDUX instead of twelve shuffles: costs are
+                // non-negative floats (|.| maxima plus non-negative penalties; +inf for padding), whose bit patterns
+                // order like unsigned integers; the lowest index among the lanes holding the minimum breaks ties
+                const unsigned kb = __reduce_min_sync(0xffffffffu, __float_as_uint(best));
+                bj = (int)__reduce_min_sync(0xffffffffu, __float_as_uint(best) == kb ? (unsigned)bj : 0x7fffffffu);
+                best = __uint_as_float(kb);
                 if (lane < DP_CLUSTER) {  // lane c sends the pair into CTA c and signals its barrier
                     const unsigned dst = r_pairs + (unsigned)(((size_t)wr * k + i) * sizeof(float2));
                     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
