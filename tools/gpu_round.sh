@@ -11,7 +11,7 @@ timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; ech
 cat gpurun_out/bench.json
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 cat gpurun_out/bench_ref.json
-timeout 300 python gpurun_probe.py > gpurun_out/probe.log 2>&1
+timeout 300 python tools/probe_kernels.py > gpurun_out/probe.log 2>&1
 cat gpurun_out/probe.log
 kill $SMI
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1

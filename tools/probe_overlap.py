@@ -23,7 +23,7 @@ def timeit(fn,n=40):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1)/n
 fa=lambda: _lib.check(lib.cppflow_lm_full_assemble(rid, prm, _lib.ptr(x0), None, _lib.ptr(problem.target_path), P, T, cu, tc, no, _lib.ptr(ws), ws.numel(), st))
-for flags,name in ((1,'deep'),(3,'compact')):
+for flags,name in ((1,"ring 3 (alone)"),(3,"ring 4 (overlap)")):
     out = xo if flags==1 else xo2
     fa(); 
     fs=lambda: _lib.check(lib.cppflow_lm_full_solve(rid, prm, _lib.ptr(x0), P, T, flags, _lib.ptr(ws), ws.numel(), _lib.ptr(out), st))
@@ -35,7 +35,7 @@ for flags,name in ((1,'deep'),(3,'compact')):
 fa(); _lib.check(lib.cppflow_lm_full_solve(rid, prm, _lib.ptr(x0), P, T, 1, _lib.ptr(ws), ws.numel(), _lib.ptr(xo), st))
 fa(); _lib.check(lib.cppflow_lm_full_solve(rid, prm, _lib.ptr(x0), P, T, 3, _lib.ptr(ws), ws.numel(), _lib.ptr(xo2), st))
 torch.cuda.synchronize()
-print('compact == deep bitwise:', bool(torch.equal(xo,xo2)))
+print('ring 4 (overlap) == ring 3 (alone) bitwise:', bool(torch.equal(xo,xo2)))
 for nch in (1,2,3,4,6,8,16):
     for ov in (True,False):
         pipe=ResidentPipeline(problem,P,all_terms_parameters(),n_chunks=nch,overlap=ov)
