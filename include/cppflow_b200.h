@@ -232,6 +232,13 @@ int cppflow_dp_search(int robot, const float* d_q, const uint8_t* d_self_flags, 
 int cppflow_path_metrics(int robot, const float* d_q, const float* d_target, int64_t P, int64_t T,
                          const float* h_cuboids, const float* h_Tcuboids, int n_obstacles, float* d_out, void* stream);
 
+/* Splits the SMs of `device` into two green contexts - the first with at least `min_sms_first` SMs (rounded up to the
+ * architecture's granularity, 8 on sm_90+), the second with the rest - and creates streams in each.  Kernels launched
+ * on a stream only run on its partition's SMs.  Used by the chunk-pipelined LM iteration to give the block solves a few
+ * SMs of their own while the assembly owns the rest (no reference counterpart). */
+int cppflow_sm_partition_create(int device, int min_sms_first, int n_streams_first, int n_streams_second,
+                                void** streams_first, void** streams_second, int* sms_first, int* sms_second);
+
 /* Measurement aid (no reference counterpart): dependent-free FP32 FMA loop on `blocks` x 1024 threads, used by
  * bench.py to measure the FP32 roofline denominator on the box.  *flops_out = FLOPs of the launch. */
 int cppflow_fp32_probe(int blocks, int iters, float* d_scratch, double* flops_out, void* stream);
