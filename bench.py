@@ -513,13 +513,27 @@ def main():
             dist.destroy_process_group()
         return
 
+    # the extra keys below must never cost the headline its line: a failure is reported in place
+    def guarded(fn, *a, **kw):
+        try:
+            return fn(*a, **kw)
+        except Exception as e:  # noqa: BLE001
+            import traceback
+
+            traceback.print_exc(file=sys.stderr)
+            return {"error": f"{type(e).__name__}: {e}"}
+
     plan = None
     plan_all = None
     if world == 1:
-        plan_all = plan_all_problems_gpu(dev)
-        plan, plan_problem, plan_qs = plan_latency_gpu(dev)
-        if not args.no_cpu_baseline:
-            plan["cpu_baseline"] = plan_latency_cpu(plan_problem, plan_qs, plan["schedule"])
+        plan_all = guarded(plan_all_problems_gpu, dev)
+        got = guarded(plan_latency_gpu, dev)
+        if isinstance(got, tuple):
+            plan, plan_problem, plan_qs = got
+            if not args.no_cpu_baseline:
+                plan["cpu_baseline"] = guarded(plan_latency_cpu, plan_problem, plan_qs, plan["schedule"])
+        else:
+            plan = got
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
