@@ -431,3 +431,80 @@ def test_resident_pipeline_sm_partition(robots):
     assert pipe.partition.sms_first >= 16 and pipe.partition.sms_first + pipe.partition.sms_second <= 148
     assert torch.equal(pipe.iterate(x0, 3), seq)
     assert torch.equal(pipe.iterate(x0, 3), seq)
+
+
+@pytest.mark.parametrize("r", ROBOTS)
+def test_empty_inputs(robots, r):
+    """Zero configurations / zero paths: every entry point returns an empty result of the right shape, no launch."""
+    from cppflow_b200 import ops
+    from cppflow_b200.lm_hyper_parameters import ALT_LOSS_V2_1_DIFF, ALT_LOSS_V2_1_POSE
+
+    rob = robots[r]
+    D = rob.ndof
+    x = torch.empty((0, D), device=DEV)
+    m, target, _ = synthetic_problem(r, 1, 12, seed=2)
+    target = target.to(DEV)
+    cuboids, Tcuboids = cuboid_tensors(OBSTACLES[r])
+    ob = ops.Obstacles(cuboids, Tcuboids)
+    assert rob.forward_kinematics(x).shape == (0, 7)
+    assert rob.jacobian(x).shape == (0, 6, D)
+    assert rob.self_collision_distances(x).shape[0] == 0
+    s, e = ops.collision_flags(rob.robot_id, D, x, ob)
+    assert s.numel() == 0 and e.numel() == 0
+    assert ops.lm_pose_step(rob.robot_id, D, ops.make_params(ALT_LOSS_V2_1_POSE), x, target, True).shape == (0, D)
+    assert ops.lm_full_step(rob.robot_id, D, ops.make_params(ALT_LOSS_V2_1_DIFF), x, None, target, 0, 12, ob, True).shape == (0, D)
+    assert ops.path_metrics(rob.robot_id, D, x, target, 0, 12, ob).shape == (0, 8)
+
+
+@pytest.mark.parametrize("r", ROBOTS)
+def test_joint_limit_corners(robots, r):
+    """FK / Jacobian / capsule distances at the corners of the joint-limit box and at the all-zero configuration
+    (data_type_utils.py:68-73 relies on FK at q = 0): the extremes of every trigonometric argument the kernels see."""
+    m = R.get_model(r)
+    lim = torch.tensor(m.actuated_joints_limits, dtype=torch.float64)
+    D = lim.shape[0]
+    corners = [torch.where(torch.tensor([(i >> d) & 1 for d in range(D)], dtype=torch.bool), lim[:, 1], lim[:, 0])
+               for i in range(0, 2 ** D, max(1, 2 ** D // 64))]
+    x = torch.stack(corners + [torch.zeros(D, dtype=torch.float64), lim.mean(dim=1)]).float()
+    pose = robots[r].forward_kinematics(x.to(DEV)).cpu().double()
+    ref = K.forward_kinematics(m, x.double())
+    assert (pose[:, :3] - ref[:, :3]).abs().max() < 1e-5
+    assert (quat_align(pose[:, 3:], ref[:, 3:]) - ref[:, 3:]).abs().max() < 1e-5
+    J = robots[r].jacobian(x.to(DEV)).cpu().double()
+    assert (J - K.jacobian(m, x.double())).abs().max() < 1e-5
+    d = robots[r].self_collision_distances(x.to(DEV)).cpu().double()
+    assert (d - G.self_collision_distances(m, x.double())).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_rotated_cuboids(robots, seed):
+    """Capsule-cuboid distances and flags against the oracle for random cuboid sizes, positions and rotations about
+    random axes (the reference asserts zero rotation, data_type_utils.py:108; the kernels take the full 4x4 pose)."""
+    from cppflow_b200 import ops
+
+    g = torch.Generator().manual_seed(100 + seed)
+    r = ROBOTS[seed % len(ROBOTS)]
+    m = R.get_model(r)
+    x = random_configs(m, 1500, seed=20 + seed)
+    cuboids, Tcuboids = [], []
+    for _ in range(3):
+        half = 0.05 + 0.25 * torch.rand(3, generator=g)
+        axis = torch.randn(3, generator=g)
+        axis = axis / axis.norm()
+        ang = float(torch.rand(1, generator=g)) * 3.0
+        Kx = torch.tensor([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+        Rm = torch.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * (Kx @ Kx)
+        Tc = torch.eye(4)
+        Tc[:3, :3] = Rm
+        Tc[:3, 3] = torch.tensor([0.2, 0.0, 0.5]) + 0.5 * (torch.rand(3, generator=g) - 0.5)
+        cuboids.append(torch.cat([-half, half]))
+        Tcuboids.append(Tc)
+    dmin = None
+    for c, Tc in zip(cuboids, Tcuboids):
+        d = robots[r].env_collision_distances(x.to(DEV), c, Tc).cpu().double()
+        d_ref = G.env_collision_distances(m, x.double(), c.double(), Tc.double())
+        assert (d - d_ref).abs().max() < 1e-5
+        dmin = d_ref.min(dim=1).values if dmin is None else torch.minimum(dmin, d_ref.min(dim=1).values)
+    _, e = ops.collision_flags(robots[r].robot_id, robots[r].ndof, x.to(DEV), ops.Obstacles(cuboids, Tcuboids))
+    clear = dmin.abs() > 1e-6
+    assert torch.equal(e.cpu().bool()[clear], (dmin < 0)[clear])
