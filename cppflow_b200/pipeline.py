@@ -23,21 +23,30 @@ from .lm_hyper_parameters import OptimizationParameters, all_terms_parameters
 
 class HostPipeline:
     def __init__(self, problem: Problem, n_paths: int, params: Optional[OptimizationParameters] = None,
-                 n_chunks: int = 16, n_run_streams: int = 4, device=None, use_graph: bool = True, overlap: bool = True):
+                 n_chunks: int = 16, n_run_streams: int = 4, device=None, use_graph: bool = True, overlap: bool = True,
+                 taper=None):
+        """`taper`: path counts of extra small chunks at BOTH ends of the chunk list, e.g. (64, 192): the first result
+        can only leave for the host one chunk latency (copy-in + assembly + the solve's ~0.25 ms chain) after the
+        start, and the last chunk's latency is exposed after the last copy-in - small first and last chunks shorten both."""
         self.problem = problem
         self.robot = problem.robot
         self.T = problem.n_timesteps
         self.P = n_paths
         self.device = problem.target_path.device if device is None else torch.device(device)
         self.prm = ops.make_params(params if params is not None else all_terms_parameters())
-        n_chunks = max(1, min(n_chunks, n_paths))
-        base, rem = divmod(n_paths, n_chunks)
+        taper = [int(t) for t in (taper or []) if t > 0]
+        if 4 * sum(taper) > n_paths:
+            taper = []
+        n_main = n_paths - 2 * sum(taper)
+        n_chunks = max(1, min(n_chunks, n_main))
+        base, rem = divmod(n_main, n_chunks)
+        sizes = taper + [base + (1 if c < rem else 0) for c in range(n_chunks)] + taper[::-1]
         self.chunks = []
         start = 0
-        for c in range(n_chunks):
-            n = base + (1 if c < rem else 0)
+        for n in sizes:
             self.chunks.append((start, n))
             start += n
+        assert start == n_paths
         D = self.robot.ndof
         self.x_dev = torch.empty((n_paths * self.T, D), device=self.device, dtype=torch.float32)
         self.out_dev = torch.empty_like(self.x_dev)
