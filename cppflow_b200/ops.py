@@ -203,7 +203,7 @@ def lm_full_step(rid: int, ndof: int, params: LmParamsC, q: torch.Tensor, xv: Op
                  out: Optional[torch.Tensor] = None, overlap: bool = False,
                  workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """levenberg_marquardt_full (+ clamp) for P paths of T waypoints on the current stream.  `overlap`: launch the
-    solve with CPPFLOW_LM_OVERLAP (compact footprint, high launch priority) - for callers that run several chunks
+    solve with CPPFLOW_LM_OVERLAP (footprint that fits next to an assembly CTA, high launch priority) - for callers that run several chunks
     of paths on several streams (pipeline.ResidentPipeline), which must also pass one `workspace` per stream."""
     q = _check_q(q, ndof)
     assert q.shape[0] == P * T, f"x must have P*T = {P * T} rows, has {q.shape[0]}"

@@ -148,7 +148,7 @@ int cppflow_lm_full_solve(int robot, const cppflow_lm_params* params, const floa
                           int do_clamp, void* d_workspace, size_t workspace_bytes, float* d_x_out, void* stream);
 
 /* `do_clamp` of cppflow_lm_full_step / cppflow_lm_full_solve is a bit set: CPPFLOW_LM_CLAMP (= 1, the reference's
- * clamp_to_joint_limits after the step) | CPPFLOW_LM_OVERLAP: the solve is launched with the compact shared-memory
+ * clamp_to_joint_limits after the step) | CPPFLOW_LM_OVERLAP: the solve is launched with a shared-memory
  * footprint (fits on an SM next to one assembly CTA) and the highest launch priority, so that it runs UNDER the
  * assembly of another chunk of paths enqueued on another stream (same results bit for bit). */
 #define CPPFLOW_LM_CLAMP 1
