@@ -66,6 +66,8 @@ struct LoopState {
     int last_valid_idx = -1, n_tls = 0, i = 0, n_sched = 0;
     double last_tl = 0.0;
     std::chrono::steady_clock::time_point t0;
+    float* metrics_dst = nullptr;  // where the metrics kernel writes: the pinned host buffer itself when the device can
+    bool zero_copy = false;        // address it (no copy engine round trip per iteration), the device scratch otherwise
 
     int init(const cppflow_lm_loop_job* j) {
         job = j;
@@ -88,6 +90,13 @@ struct LoopState {
         row_bytes = (size_t)j->T * ndof * sizeof(float);
         cudaError_t e = cudaMemcpyAsync(x_cur, j->d_x_seed, row_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)j->stream);
         if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "lm_alternating_loss: %s", cudaGetErrorString(e));
+        // page-locked host memory is device-addressable under unified addressing: let the 8 metrics of an iterate land
+        // there directly (a 32-byte write over PCIe at the end of the kernel) instead of copying them afterwards
+        cudaPointerAttributes pa;
+        zero_copy = cudaPointerGetAttributes(&pa, j->h_pinned_metrics) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+                    pa.devicePointer != nullptr;
+        if (!zero_copy) cudaGetLastError();  // unregistered host memory reports an error: not fatal, copy instead
+        metrics_dst = zero_copy ? (float*)pa.devicePointer : d_metrics;
         t0 = std::chrono::steady_clock::now();
         done = j->max_n_steps == 0;
         return CPPFLOW_OK;
@@ -109,10 +118,12 @@ struct LoopState {
         if (n_sched < CPPFLOW_LM_SCHEDULE_MAX - 1) j->result->schedule[n_sched++] = was_differencing ? 'd' : 'p';
         float* tmp = x_cur; x_cur = x_new; x_new = tmp;  // clamp_to_joint_limits is fused into both steps (:259)
         if (int rc = cppflow_path_metrics(j->robot, x_cur, j->d_target, 1, j->T, j->h_cuboids, j->h_Tcuboids, j->n_obstacles,
-                                          d_metrics, j->stream))
+                                          metrics_dst, j->stream))
             return rc;
-        cudaError_t e = cudaMemcpyAsync(j->h_pinned_metrics, d_metrics, 8 * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)j->stream);
-        if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "lm_alternating_loss: %s", cudaGetErrorString(e));
+        if (!zero_copy) {
+            cudaError_t e = cudaMemcpyAsync(j->h_pinned_metrics, d_metrics, 8 * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)j->stream);
+            if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "lm_alternating_loss: %s", cudaGetErrorString(e));
+        }
         return CPPFLOW_OK;
     }
 
