@@ -57,6 +57,10 @@ inline int make_obstacles(const float* h_cuboids, const float* h_Tcuboids, int n
     return CPPFLOW_OK;
 }
 
+// cppflow_path_metrics with a completion tag in column 7 of every row (k_metrics.cu)
+int path_metrics_tagged(int robot, const float* d_q, const float* d_target, int64_t P, int64_t T, const float* h_cuboids,
+                        const float* h_Tcuboids, int n_obstacles, float* d_out, float tag, void* stream);
+
 inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
 }  // namespace cppflow

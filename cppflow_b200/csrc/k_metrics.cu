@@ -42,7 +42,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <class M, bool CLUSTERED>
 __global__ void __launch_bounds__(MBLOCK)
 path_metrics_kernel(const float* __restrict__ q, const float* __restrict__ target, int64_t T, const Obstacles ob,
-                    float* __restrict__ out) {
+                    float* __restrict__ out, float tag) {
     constexpr int D = M::NDOF;
     extern __shared__ float smem[];
     __shared__ float red[7][MBLOCK / 32];
@@ -124,7 +124,8 @@ path_metrics_kernel(const float* __restrict__ q, const float* __restrict__ targe
             float* o = out + p * 8;
 #pragma unroll
             for (int k = 0; k < 7; ++k) o[k] = r[k];
-            o[7] = 0.f;
+            __threadfence_system();  // `out` may be host memory polled by the CPU: the tag must not overtake the metrics
+            *reinterpret_cast<volatile float*>(o + 7) = tag;
         }
     }
     if constexpr (CLUSTERED) {
@@ -143,7 +144,8 @@ path_metrics_kernel(const float* __restrict__ q, const float* __restrict__ targe
             float* o = out + p * 8;
 #pragma unroll
             for (int k = 0; k < 7; ++k) o[k] = r[k];
-            o[7] = 0.f;
+            __threadfence_system();
+            *reinterpret_cast<volatile float*>(o + 7) = tag;
         }
     }
 }
@@ -152,9 +154,11 @@ path_metrics_kernel(const float* __restrict__ q, const float* __restrict__ targe
 
 using namespace cppflow;
 
-extern "C" int cppflow_path_metrics(int robot, const float* d_q, const float* d_target, int64_t P, int64_t T,
-                                    const float* h_cuboids, const float* h_Tcuboids, int n_obstacles, float* d_out,
-                                    void* stream) {
+// `tag` is written to out[p][7] after the seven metrics (system-scope fence in between): a host thread polling a
+// device-mapped output buffer sees a complete row once the tag shows up (lm_loop.cu)
+int cppflow::path_metrics_tagged(int robot, const float* d_q, const float* d_target, int64_t P, int64_t T,
+                                 const float* h_cuboids, const float* h_Tcuboids, int n_obstacles, float* d_out, float tag,
+                                 void* stream) {
     CPPFLOW_CHECK_ARG(P >= 0 && T > 0, "P, T");
     if (P == 0) return CPPFLOW_OK;
     CPPFLOW_CHECK_ARG(d_q && d_target && d_out, "null pointer");
@@ -178,12 +182,18 @@ extern "C" int cppflow_path_metrics(int robot, const float* d_q, const float* d_
             at[0].val.clusterDim.z = 1;
             cfg.attrs = at;
             cfg.numAttrs = 1;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, path_metrics_kernel<M, true>, d_q, d_target, T, ob, d_out);
+            cudaError_t e = cudaLaunchKernelEx(&cfg, path_metrics_kernel<M, true>, d_q, d_target, T, ob, d_out, tag);
             if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "path_metrics cluster launch: %s", cudaGetErrorString(e));
         } else {
-            path_metrics_kernel<M, false><<<(unsigned)P, MBLOCK, sh, (cudaStream_t)stream>>>(d_q, d_target, T, ob, d_out);
+            path_metrics_kernel<M, false><<<(unsigned)P, MBLOCK, sh, (cudaStream_t)stream>>>(d_q, d_target, T, ob, d_out, tag);
         }
     });
     CPPFLOW_CHECK_LAUNCH();
     return CPPFLOW_OK;
+}
+
+extern "C" int cppflow_path_metrics(int robot, const float* d_q, const float* d_target, int64_t P, int64_t T,
+                                    const float* h_cuboids, const float* h_Tcuboids, int n_obstacles, float* d_out,
+                                    void* stream) {
+    return cppflow::path_metrics_tagged(robot, d_q, d_target, P, T, h_cuboids, h_Tcuboids, n_obstacles, d_out, 0.f, stream);
 }

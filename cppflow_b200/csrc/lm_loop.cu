@@ -8,6 +8,7 @@
 // is 8 floats into page-locked memory and one cudaStreamSynchronize; the kernel launches, the decision logic and the
 // bookkeeping of an iteration cost ~10 us of host time instead of ~55 us when driven from Python through ctypes
 // (the per-plan latency of fetch__circle is dominated by these 20 round trips, not by the kernels).
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <vector>
@@ -66,6 +67,7 @@ struct LoopState {
     int last_valid_idx = -1, n_tls = 0, i = 0, n_sched = 0;
     double last_tl = 0.0;
     std::chrono::steady_clock::time_point t0;
+    float tag = 0.f;               // completion tag of the iteration in flight (i + 1)
     float* metrics_dst = nullptr;  // where the metrics kernel writes: the pinned host buffer itself when the device can
     bool zero_copy = false;        // address it (no copy engine round trip per iteration), the device scratch otherwise
 
@@ -117,8 +119,10 @@ struct LoopState {
         }
         if (n_sched < CPPFLOW_LM_SCHEDULE_MAX - 1) j->result->schedule[n_sched++] = was_differencing ? 'd' : 'p';
         float* tmp = x_cur; x_cur = x_new; x_new = tmp;  // clamp_to_joint_limits is fused into both steps (:259)
-        if (int rc = cppflow_path_metrics(j->robot, x_cur, j->d_target, 1, j->T, j->h_cuboids, j->h_Tcuboids, j->n_obstacles,
-                                          metrics_dst, j->stream))
+        tag = (float)(i + 1);
+        if (zero_copy) *reinterpret_cast<volatile float*>(j->h_pinned_metrics + 7) = 0.f;  // not this iteration's tag
+        if (int rc = path_metrics_tagged(j->robot, x_cur, j->d_target, 1, j->T, j->h_cuboids, j->h_Tcuboids, j->n_obstacles,
+                                         metrics_dst, tag, j->stream))
             return rc;
         if (!zero_copy) {
             cudaError_t e = cudaMemcpyAsync(j->h_pinned_metrics, d_metrics, 8 * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)j->stream);
@@ -129,7 +133,22 @@ struct LoopState {
 
     int finish() {
         const cppflow_lm_loop_job* j = job;
-        cudaError_t e = cudaStreamSynchronize((cudaStream_t)j->stream);  // the one host round trip of the iteration
+        // the one host round trip of the iteration.  With the metrics landing in host memory the CPU polls their tag
+        // (~1 us after the kernel's last store) instead of going through cudaStreamSynchronize; if the tag does not
+        // show up within a second - a faulting kernel never writes it - the stream is synchronised for the error.
+        cudaError_t e = cudaSuccess;
+        bool seen = false;
+        if (zero_copy) {
+            const volatile float* flag = j->h_pinned_metrics + 7;
+            const auto t_poll = std::chrono::steady_clock::now();
+            for (unsigned spin = 0; !(seen = (*flag == tag)); ++spin) {
+                if ((spin & 0xfff) == 0xfff &&
+                    std::chrono::duration<double>(std::chrono::steady_clock::now() - t_poll).count() > 1.0)
+                    break;
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+        }
+        if (!seen) e = cudaStreamSynchronize((cudaStream_t)j->stream);
         if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "lm_alternating_loss: %s", cudaGetErrorString(e));
         const float* m = j->h_pinned_metrics;  // max_pos_cm, max_rot_deg, mjac_deg, mjac_cm, tl, min_self, min_env
         const double tl_new = m[4];
