@@ -21,6 +21,9 @@ from .lm_hyper_parameters import ALT_LOSS_V2_1_DIFF, ALT_LOSS_V2_1_POSE, Optimiz
 from .optimization_utils import LmResidualFns, clamp_to_joint_limits, path_metrics, x_is_valid
 
 
+_SEED_STREAMS: Dict[str, list] = {}
+
+
 @dataclass
 class OptimizationProblem:
     problem: Problem
@@ -229,6 +232,28 @@ def run_lm_optimization(problem: Problem, x_seed: torch.Tensor, tmax_sec: float,
     assert stacked_target_path.shape[0] == x_seed.shape[0]
     assert x_seed.shape[1] == problem.robot.ndof
     assert isinstance(max_n_steps, int), f"error: max_n_steps must be int, is {type(max_n_steps)}"
+    if parallel_count > 1:
+        # the reference stacks `parallel_count` seeds but its full LM step asserts parallel_count == 1 (:128); here
+        # every seed runs its own alternating loop, all in lock step on their own streams, and the first valid one
+        # (lowest seed index) is returned - the first seed's last iterate if none is valid
+        assert mesh_validator is None, "parallel seeds run inside the library: no mesh callback"
+        T = problem.n_timesteps
+        seeds = [x_seed[i * T:(i + 1) * T].contiguous() for i in range(parallel_count)]
+        pool = _SEED_STREAMS.setdefault(str(x_seed.device), [])
+        while len(pool) < parallel_count:
+            pool.append(torch.cuda.Stream(x_seed.device))
+        cur = torch.cuda.current_stream(x_seed.device)
+        for s in pool[:parallel_count]:
+            s.wait_stream(cur)
+        results = run_lm_optimization_many([problem] * parallel_count, seeds, pool[:parallel_count], tmax_sec, max_n_steps,
+                                           return_if_valid_after_n_steps, convergence_threshold)
+        for s in pool[:parallel_count]:
+            cur.wait_stream(s)
+        for i, r in enumerate(results):
+            if r.is_valid:
+                r.parallel_seed_idx = i
+                return r
+        return results[0]
     opt_problem = OptimizationProblem(problem, problem.constraints, x_seed, stacked_target_path, verbosity,
                                       parallel_count, results_df)
     opt_state = OptimizationState(x_seed.clone(), 0, time())

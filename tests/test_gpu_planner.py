@@ -196,3 +196,29 @@ def test_config4_plan_many_concurrent_equals_sequential():
             assert a.plan.is_valid == b.plan.is_valid, name
             assert torch.equal(a.plan.q_path, b.plan.q_path), name
             assert a.debug_info.get("n_optimization_steps") == b.debug_info.get("n_optimization_steps"), name
+
+
+def test_run_lm_optimization_parallel_seeds():
+    """run_lm_optimization(parallel_count = 3): every stacked seed runs its own alternating loop (lock step, own
+    streams); the result is the first valid seed's, identical to refining that seed alone."""
+    from cppflow_b200.collision_detection import qpaths_batched_collisions
+    from cppflow_b200.optimization import run_lm_optimization
+    from cppflow_b200.planners import LmIkCandidateGenerator
+    from cppflow_b200.search import dp_search
+
+    problem = _problem("fetch_arm__s")
+    T = problem.n_timesteps
+    qs = LmIkCandidateGenerator(seed=1)(problem, 64).contiguous()
+    self_v, env_v = qpaths_batched_collisions(problem, qs)
+    best = dp_search(problem.robot, qs, self_v, env_v, verbosity=0).to(DEV).contiguous()
+    bad = best.clone()
+    bad[T // 2:] = bad[T // 2:].flip(0)  # a seed with a jump in the middle: takes more steps, may stay invalid
+    stacked = torch.cat([bad, best, qs[0]], dim=0).contiguous()
+    kw = dict(max_n_steps=20, tmax_sec=30.0, return_if_valid_after_n_steps=0, convergence_threshold=1e6, verbosity=0)
+    singles = [run_lm_optimization(problem, s.contiguous(), **kw) for s in (bad, best, qs[0].contiguous())]
+    res = run_lm_optimization(problem, stacked, parallel_count=3, **kw)
+    expect = next((i for i, r in enumerate(singles) if r.is_valid), 0)
+    assert singles[1].is_valid
+    assert res.parallel_seed_idx == (expect if singles[expect].is_valid else 0)
+    assert res.is_valid == singles[expect].is_valid and res.schedule == singles[expect].schedule
+    assert torch.equal(res.x_opt, singles[expect].x_opt)
