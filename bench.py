@@ -327,7 +327,10 @@ def main():
     robot = get_robot("fetch")
     P, T, D = args.paths, args.waypoints, robot.ndof
     problem = synthetic_problem(robot, T, seed=0, device=dev)
-    _, x_host = synthetic_seeds_host(robot, P, T, seed=0, shard=rank, pin=True)
+    from cppflow_b200.pipeline import numa_local
+
+    with numa_local(dev):  # page-locked buffers on the GPU's own NUMA node
+        _, x_host = synthetic_seeds_host(robot, P, T, seed=0, shard=rank, pin=True)
     x0 = x_host.to(dev)
     x_out = torch.empty_like(x0)
     prm = ops.make_params(all_terms_parameters())
@@ -394,7 +397,8 @@ def main():
     from cppflow_b200.pipeline import HostPipeline
 
     pipe = HostPipeline(problem, P, all_terms_parameters())
-    out_host = torch.empty_like(x_host).pin_memory()
+    with numa_local(dev):
+        out_host = torch.empty_like(x_host).pin_memory()
     e2e_steps = max(3, min(args.steps, 20))
     for _ in range(2):
         pipe.refine(x_host, out_host)
