@@ -176,3 +176,15 @@ def test_split_paths_covers_every_path_once():
         gran = 256 if n >= 256 * c else 16 if n >= 16 * c else 1
         assert all(k % gran == 0 for _, k in chunks[:-1])
     assert split_paths(8192, 4) == [(0, 2048), (2048, 2048), (4096, 2048), (6144, 2048)]
+
+
+def test_numa_local_is_a_safe_no_op_without_topology():
+    """pipeline.numa_local must never raise and must restore the affinity (no CUDA device / no sysfs entry here)."""
+    import os
+
+    from cppflow_b200.pipeline import numa_local
+
+    before = os.sched_getaffinity(0)
+    with numa_local("cuda:0"):
+        pass
+    assert os.sched_getaffinity(0) == before
