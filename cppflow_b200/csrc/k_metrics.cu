@@ -9,7 +9,7 @@
 // alternating LM loop checks ONE path per iteration and waits for the answer) the waypoints of a path are split over
 // the CTAs of a thread-block cluster instead, one pass of 128 waypoints each; the per-CTA partial results are written
 // into the shared memory of the cluster's CTA 0 (distributed shared memory) and combined there in rank order, so the
-// sums stay deterministic: 41 -> ~15 us for T = 295.
+// sums stay deterministic; in that variant four lanes share a waypoint's 68 distance tests: 41 -> 20 -> ~12 us for T = 295.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -39,7 +39,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // CLUSTERED: gridDim.x = P * S with clusters of S CTAs; CTA `rank` of a cluster takes the waypoints
 // rank * MBLOCK + threadIdx.x + j * S * MBLOCK of path blockIdx.x / S
-template <class M, bool CLUSTERED>
+// G lanes per waypoint (clustered variant: 4): every lane of a group runs the FK into its own shared-memory column and
+// takes every G-th capsule pair / capsule-cuboid test; the warp reductions at the end combine the lanes (max and min
+// are idempotent, the trajectory length is added by lane 0 of a group only).
+template <class M, bool CLUSTERED, int G>
 __global__ void __launch_bounds__(MBLOCK)
 path_metrics_kernel(const float* __restrict__ q, const float* __restrict__ target, int64_t T, const Obstacles ob,
                     float* __restrict__ out, float tag) {
@@ -56,7 +59,8 @@ path_metrics_kernel(const float* __restrict__ q, const float* __restrict__ targe
     const int64_t p = blockIdx.x / csize;
     float* sm = smem + threadIdx.x;
     float m_pos = 0.f, m_rot = 0.f, m_rev = 0.f, m_pri = 0.f, tl = 0.f, d_self = INFINITY, d_env = INFINITY;
-    for (int64_t t = rank * MBLOCK + threadIdx.x; t < T; t += (int64_t)csize * MBLOCK) {
+    const int gl = threadIdx.x % G;  // lane within the waypoint's group
+    for (int64_t t = rank * (MBLOCK / G) + threadIdx.x / G; t < T; t += (int64_t)csize * (MBLOCK / G)) {
         const int64_t i = p * T + t;
         float x[D];
 #pragma unroll
@@ -83,19 +87,19 @@ path_metrics_kernel(const float* __restrict__ q, const float* __restrict__ targe
                 } else {
                     const float w = fabsf(wrap_pi(x[d] - prev));
                     m_rev = fmaxf(m_rev, w * 57.29577951308232f);
-                    tl += w;
+                    if (gl == 0) tl += w;
                 }
             });
         }
-        for (int pr = 0; pr < M::NPAIR; ++pr) {
+        for (int pr = gl; pr < M::NPAIR; pr += G) {
             float C2[3], nrm[3];
             d_self = fminf(d_self, self_pair_distance<M, MBLOCK>(sm, pr, C2, nrm, d_self));
         }
-        for (int o = 0; o < ob.n; ++o)
-            for (int c = 0; c < M::NCAP; ++c) {
-                float Cw[3], nrm[3];
-                d_env = fminf(d_env, env_capsule_distance<M, MBLOCK>(sm, c, ob, o, Cw, nrm, d_env));
-            }
+        for (int it = gl; it < ob.n * M::NCAP; it += G) {
+            const int o = it / M::NCAP, c = it - o * M::NCAP;
+            float Cw[3], nrm[3];
+            d_env = fminf(d_env, env_capsule_distance<M, MBLOCK>(sm, c, ob, o, Cw, nrm, d_env));
+        }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float v[7] = {warp_max(m_pos), warp_max(m_rot), warp_max(m_rev), warp_max(m_pri), warp_sum(tl), warp_min(d_self),
@@ -164,8 +168,11 @@ int cppflow::path_metrics_tagged(int robot, const float* d_q, const float* d_tar
     CPPFLOW_CHECK_ARG(d_q && d_target && d_out, "null pointer");
     Obstacles ob;
     if (int rc = make_obstacles(h_cuboids, h_Tcuboids, n_obstacles, ob)) return rc;
-    // few paths: split each path over a cluster of up to 8 CTAs (one pass of MBLOCK waypoints per CTA)
-    const int csize = (int)((T + MBLOCK - 1) / MBLOCK < 8 ? (T + MBLOCK - 1) / MBLOCK : 8);
+    // few paths: split each path over a cluster of up to 8 CTAs with G lanes per waypoint, G the largest of 4 / 2 / 1
+    // for which the path still fits ONE pass of the cluster (8 * MBLOCK / G waypoints)
+    const int G = T <= 8 * MBLOCK / 4 ? 4 : (T <= 8 * MBLOCK / 2 ? 2 : 1);
+    const int64_t per_cta = MBLOCK / G;
+    const int csize = (int)((T + per_cta - 1) / per_cta < 8 ? (T + per_cta - 1) / per_cta : 8);
     const bool clustered = csize > 1 && P * csize <= 2 * 148;
     CPPFLOW_DISPATCH_ROBOT(robot, {
         const size_t sh = sizeof(float) * MBLOCK * SmemLayout<M>::N_DIST;
@@ -182,10 +189,12 @@ int cppflow::path_metrics_tagged(int robot, const float* d_q, const float* d_tar
             at[0].val.clusterDim.z = 1;
             cfg.attrs = at;
             cfg.numAttrs = 1;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, path_metrics_kernel<M, true>, d_q, d_target, T, ob, d_out, tag);
+            cudaError_t e = G == 4   ? cudaLaunchKernelEx(&cfg, path_metrics_kernel<M, true, 4>, d_q, d_target, T, ob, d_out, tag)
+                            : G == 2 ? cudaLaunchKernelEx(&cfg, path_metrics_kernel<M, true, 2>, d_q, d_target, T, ob, d_out, tag)
+                                     : cudaLaunchKernelEx(&cfg, path_metrics_kernel<M, true, 1>, d_q, d_target, T, ob, d_out, tag);
             if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "path_metrics cluster launch: %s", cudaGetErrorString(e));
         } else {
-            path_metrics_kernel<M, false><<<(unsigned)P, MBLOCK, sh, (cudaStream_t)stream>>>(d_q, d_target, T, ob, d_out, tag);
+            path_metrics_kernel<M, false, 1><<<(unsigned)P, MBLOCK, sh, (cudaStream_t)stream>>>(d_q, d_target, T, ob, d_out, tag);
         }
     });
     CPPFLOW_CHECK_LAUNCH();
