@@ -51,3 +51,23 @@ print(f'pipeline structure, 16 chunks, 30 elementwise kernels per chunk: {t(lamb
 def sleepy(a,b):
     torch.cuda._sleep(int(0.28e-3*1.9e9)); torch.mul(a,2,out=b)
 print(f'pipeline structure, 16 chunks, 0.28 ms spin kernel per chunk (latency like the LM step, no memory traffic): {t(lambda: piped(16, sleepy)):.3f} ms')
+# two copy streams per direction, alternating chunks (can the copy engine's wait for chunk c+1 overlap the copy of chunk c?)
+s_in2=[torch.cuda.Stream() for _ in range(2)]; s_out2=[torch.cuda.Stream() for _ in range(2)]
+def piped2(nch, work, n_in=2, n_out=2):
+    cur=torch.cuda.current_stream()
+    for s in s_in2+s_out2+s_run: s.wait_stream(cur)
+    c=n//nch
+    for i in range(nch):
+        sl=slice(i*c,(i+1)*c)
+        e1=torch.cuda.Event(); e2=torch.cuda.Event()
+        si=s_in2[i%n_in]; so=s_out2[i%n_out]
+        with torch.cuda.stream(si): d1[sl].copy_(xh[sl],non_blocking=True); e1.record(si)
+        sr=s_run[i%4]
+        with torch.cuda.stream(sr):
+            sr.wait_event(e1); work(d1[sl],d2[sl]); e2.record(sr)
+        with torch.cuda.stream(so):
+            so.wait_event(e2); oh[sl].copy_(d2[sl],non_blocking=True)
+    for s in s_in2+s_out2+s_run: cur.wait_stream(s)
+triv=lambda a,b: torch.mul(a,2,out=b)
+for n_in,n_out in ((1,1),(1,2),(2,1),(2,2)):
+    print(f'pipeline structure, 16 chunks, trivial kernel, {n_in} copy-in / {n_out} copy-out streams: {t(lambda: piped2(16, triv, n_in, n_out)):.3f} ms')
