@@ -61,6 +61,11 @@ inline int make_obstacles(const float* h_cuboids, const float* h_Tcuboids, int n
 int path_metrics_tagged(int robot, const float* d_q, const float* d_target, int64_t P, int64_t T, const float* h_cuboids,
                         const float* h_Tcuboids, int n_obstacles, float* d_out, float tag, void* stream);
 
+// pose-only LM step of one path (T <= 1024) fused with the metrics of the new path (k_metrics.cu)
+int pose_step_metrics_tagged(int robot, const cppflow_lm_params* params, const float* d_q, const float* d_target, int64_t T,
+                             const float* h_cuboids, const float* h_Tcuboids, int n_obstacles, float* d_x_out, float* d_out,
+                             float tag, void* stream);
+
 inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
 }  // namespace cppflow

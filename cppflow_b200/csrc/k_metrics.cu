@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "collision.cuh"
+#include "pose_step.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -42,10 +43,24 @@ __device__ __forceinline__ float warp_sum(float v) {
 // G lanes per waypoint (clustered variant: 4): every lane of a group runs the FK into its own shared-memory column and
 // takes every G-th capsule pair / capsule-cuboid test; the warp reductions at the end combine the lanes (max and min
 // are idempotent, the trajectory length is added by lane 0 of a group only).
-template <class M, bool CLUSTERED, int G>
+// FUSE (clustered, one pass over the path, one path): the kernel first takes the pose-only LM step of every waypoint
+// (lane 0 of a waypoint's group; pose_step.cuh) from `q` into `pf.x_out`, and then evaluates the metrics of the NEW path -
+// one launch per iteration of the single-path LM loop instead of two launch-bound ones.
+struct PoseFuse {
+    float alpha_pos, alpha_rot, lambda;
+    float* x_out;
+};
+
+template <bool COHERENT>
+__device__ __forceinline__ float ld_row(const float* p) {
+    if constexpr (COHERENT) return __ldcg(p);  // written earlier in this kernel by another SM of the cluster
+    else return __ldg(p);
+}
+
+template <class M, bool CLUSTERED, int G, bool FUSE = false>
 __global__ void __launch_bounds__(MBLOCK)
-path_metrics_kernel(const float* __restrict__ q, const float* __restrict__ target, int64_t T, const Obstacles ob,
-                    float* __restrict__ out, float tag) {
+path_metrics_kernel(const float* __restrict__ q_in, const float* __restrict__ target, int64_t T, const Obstacles ob,
+                    float* __restrict__ out, float tag, const PoseFuse pf) {
     constexpr int D = M::NDOF;
     extern __shared__ float smem[];
     __shared__ float red[7][MBLOCK / 32];
@@ -58,13 +73,31 @@ path_metrics_kernel(const float* __restrict__ q, const float* __restrict__ targe
     }
     const int64_t p = blockIdx.x / csize;
     float* sm = smem + threadIdx.x;
+    const float* q = q_in;
+    if constexpr (FUSE) {
+        static_assert(CLUSTERED, "the fused step needs the cluster-wide barrier");
+        // every thread takes part in the shuffles and the barrier: threads beyond the path shadow its last waypoint
+        const int64_t t0 = rank * (MBLOCK / G) + threadIdx.x / G;
+        const bool act = t0 < T;
+        const int64_t tc = act ? t0 : T - 1;
+        float xs[D], tgs[7];
+        load_q<M>(q_in, tc, xs);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) tgs[k] = __ldg(target + tc * 7 + k);
+        if (threadIdx.x % G == 0) pose_lm_update<M>(xs, tgs, pf.alpha_pos, pf.alpha_rot, pf.lambda, 1, nullptr, nullptr, 0);
+        __syncwarp();
+        if (threadIdx.x % G == 0 && act) store_q<M>(pf.x_out, tc, xs);
+        __threadfence();
+        cg::this_cluster().sync();  // the new path is complete (neighbouring waypoints live in other CTAs)
+        q = pf.x_out;
+    }
     float m_pos = 0.f, m_rot = 0.f, m_rev = 0.f, m_pri = 0.f, tl = 0.f, d_self = INFINITY, d_env = INFINITY;
     const int gl = threadIdx.x % G;  // lane within the waypoint's group
     for (int64_t t = rank * (MBLOCK / G) + threadIdx.x / G; t < T; t += (int64_t)csize * (MBLOCK / G)) {
         const int64_t i = p * T + t;
         float x[D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) x[d] = __ldg(q + i * D + d);
+        for (int d = 0; d < D; ++d) x[d] = ld_row<FUSE>(q + i * D + d);
         CollisionSink<M, MBLOCK, false> sink{sm};
         Frame F;
         fk_chain<M>(x, sink, F);
@@ -81,7 +114,7 @@ path_metrics_kernel(const float* __restrict__ q, const float* __restrict__ targe
         if (t > 0) {
             static_for<D>([&](auto Dd) {
                 constexpr int d = decltype(Dd)::value;
-                const float prev = __ldg(q + (i - 1) * D + d);
+                const float prev = ld_row<FUSE>(q + (i - 1) * D + d);
                 if constexpr (dof_is_prismatic<M>(d)) {
                     m_pri = fmaxf(m_pri, 100.f * fabsf(x[d] - prev));
                 } else {
@@ -189,13 +222,47 @@ int cppflow::path_metrics_tagged(int robot, const float* d_q, const float* d_tar
             at[0].val.clusterDim.z = 1;
             cfg.attrs = at;
             cfg.numAttrs = 1;
-            cudaError_t e = G == 4   ? cudaLaunchKernelEx(&cfg, path_metrics_kernel<M, true, 4>, d_q, d_target, T, ob, d_out, tag)
-                            : G == 2 ? cudaLaunchKernelEx(&cfg, path_metrics_kernel<M, true, 2>, d_q, d_target, T, ob, d_out, tag)
-                                     : cudaLaunchKernelEx(&cfg, path_metrics_kernel<M, true, 1>, d_q, d_target, T, ob, d_out, tag);
+            cudaError_t e = G == 4   ? cudaLaunchKernelEx(&cfg, path_metrics_kernel<M, true, 4>, d_q, d_target, T, ob, d_out, tag, PoseFuse{})
+                            : G == 2 ? cudaLaunchKernelEx(&cfg, path_metrics_kernel<M, true, 2>, d_q, d_target, T, ob, d_out, tag, PoseFuse{})
+                                     : cudaLaunchKernelEx(&cfg, path_metrics_kernel<M, true, 1>, d_q, d_target, T, ob, d_out, tag, PoseFuse{});
             if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "path_metrics cluster launch: %s", cudaGetErrorString(e));
         } else {
-            path_metrics_kernel<M, false, 1><<<(unsigned)P, MBLOCK, sh, (cudaStream_t)stream>>>(d_q, d_target, T, ob, d_out, tag);
+            path_metrics_kernel<M, false, 1><<<(unsigned)P, MBLOCK, sh, (cudaStream_t)stream>>>(d_q, d_target, T, ob, d_out, tag, PoseFuse{});
         }
+    });
+    CPPFLOW_CHECK_LAUNCH();
+    return CPPFLOW_OK;
+}
+
+// pose-only LM step (+ clamp) of ONE path of T <= 8 * MBLOCK waypoints and the metrics of the new path, one launch
+int cppflow::pose_step_metrics_tagged(int robot, const cppflow_lm_params* params, const float* d_q, const float* d_target,
+                                      int64_t T, const float* h_cuboids, const float* h_Tcuboids, int n_obstacles,
+                                      float* d_x_out, float* d_out, float tag, void* stream) {
+    CPPFLOW_CHECK_ARG(params && d_q && d_target && d_x_out && d_out, "null pointer");
+    CPPFLOW_CHECK_ARG(T > 0 && T <= 8 * MBLOCK, "T");
+    Obstacles ob;
+    if (int rc = make_obstacles(h_cuboids, h_Tcuboids, n_obstacles, ob)) return rc;
+    const int G = T <= 8 * MBLOCK / 4 ? 4 : (T <= 8 * MBLOCK / 2 ? 2 : 1);
+    const int64_t per_cta = MBLOCK / G;
+    const int csize = (int)((T + per_cta - 1) / per_cta);
+    const PoseFuse pf{params->alpha_position, params->alpha_rotation, params->lm_lambda, d_x_out};
+    CPPFLOW_DISPATCH_ROBOT(robot, {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)csize);
+        cfg.blockDim = dim3(MBLOCK);
+        cfg.dynamicSmemBytes = sizeof(float) * MBLOCK * SmemLayout<M>::N_DIST;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)csize;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaError_t e = G == 4   ? cudaLaunchKernelEx(&cfg, path_metrics_kernel<M, true, 4, true>, d_q, d_target, T, ob, d_out, tag, pf)
+                        : G == 2 ? cudaLaunchKernelEx(&cfg, path_metrics_kernel<M, true, 2, true>, d_q, d_target, T, ob, d_out, tag, pf)
+                                 : cudaLaunchKernelEx(&cfg, path_metrics_kernel<M, true, 1, true>, d_q, d_target, T, ob, d_out, tag, pf);
+        if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "pose_step_metrics launch: %s", cudaGetErrorString(e));
     });
     CPPFLOW_CHECK_LAUNCH();
     return CPPFLOW_OK;

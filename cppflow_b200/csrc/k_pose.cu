@@ -7,80 +7,9 @@
 //   levenberg_marquardt_only_pose                             (optimization.py:61-92)
 //   clamp_to_joint_limits                                     (optimization_utils.py:823-833)
 #include "common.cuh"
-#include "kinematics.cuh"
-#include "linalg.cuh"
+#include "pose_step.cuh"
 
 namespace cppflow {
-
-template <class M>
-struct JointSink {
-    float a[M::NDOF][3];
-    float o[M::NDOF][3];
-    template <int D>
-    __device__ __forceinline__ void joint(std::integral_constant<int, D>, const float* axis, const float* origin) {
-#pragma unroll
-        for (int r = 0; r < 3; ++r) { a[D][r] = axis[r]; o[D][r] = origin[r]; }
-    }
-    template <int F>
-    __device__ __forceinline__ void frame(std::integral_constant<int, F>, const Frame&) {}
-};
-
-struct NullSink {
-    template <int D>
-    __device__ __forceinline__ void joint(std::integral_constant<int, D>, const float*, const float*) {}
-    template <int F>
-    __device__ __forceinline__ void frame(std::integral_constant<int, F>, const Frame&) {}
-};
-
-template <class M>
-__device__ __forceinline__ void load_q(const float* __restrict__ q, int64_t i, float (&x)[M::NDOF]) {
-    if constexpr (M::NDOF == 8) {
-        const float4 v0 = __ldg(reinterpret_cast<const float4*>(q + i * 8));
-        const float4 v1 = __ldg(reinterpret_cast<const float4*>(q + i * 8) + 1);
-        x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
-        x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-    } else {
-#pragma unroll
-        for (int d = 0; d < M::NDOF; ++d) x[d] = __ldg(q + i * M::NDOF + d);
-    }
-}
-
-template <class M>
-__device__ __forceinline__ void store_q(float* __restrict__ q, int64_t i, const float (&x)[M::NDOF]) {
-    if constexpr (M::NDOF == 8) {
-        reinterpret_cast<float4*>(q + i * 8)[0] = make_float4(x[0], x[1], x[2], x[3]);
-        reinterpret_cast<float4*>(q + i * 8)[1] = make_float4(x[4], x[5], x[6], x[7]);
-    } else {
-#pragma unroll
-        for (int d = 0; d < M::NDOF; ++d) q[i * M::NDOF + d] = x[d];
-    }
-}
-
-template <class M>
-__device__ __forceinline__ void clamp_limits(float (&x)[M::NDOF]) {
-    static_for<M::NDOF>([&](auto Dd) {
-        constexpr int d = decltype(Dd)::value;
-        x[d] = fminf(fmaxf(x[d], dof_lower<M>(d)), dof_upper<M>(d));
-    });
-}
-
-// J[r][d], rows 0-2 angular, 3-5 linear (optimization.py:77-80)
-template <class M>
-__device__ __forceinline__ void geometric_jacobian(const JointSink<M>& js, const Frame& F, float (&J)[6][M::NDOF]) {
-    static_for<M::NDOF>([&](auto Dd) {
-        constexpr int d = decltype(Dd)::value;
-        if constexpr (dof_is_prismatic<M>(d)) {
-            J[0][d] = 0.f; J[1][d] = 0.f; J[2][d] = 0.f;
-            J[3][d] = js.a[d][0]; J[4][d] = js.a[d][1]; J[5][d] = js.a[d][2];
-        } else {
-            const float r[3] = {F.p[0] - js.o[d][0], F.p[1] - js.o[d][1], F.p[2] - js.o[d][2]};
-            float v[3];
-            cross3(js.a[d], r, v);
-            J[0][d] = js.a[d][0]; J[1][d] = js.a[d][1]; J[2][d] = js.a[d][2];
-            J[3][d] = v[0]; J[4][d] = v[1]; J[5][d] = v[2];
-        }
-    });
-}
 
 template <class M>
 __global__ void __launch_bounds__(128) fk_kernel(const float* __restrict__ q, int64_t n, float* __restrict__ poses) {
@@ -146,10 +75,7 @@ pose_error_kernel(const float* __restrict__ q, const float* __restrict__ target,
     }
 }
 
-// Pose-only LM step.  (J^T J + lambda I) dx = J^T e is solved in its dual form dx = J^T (J J^T + lambda I)^-1 e:
-// algebraically identical, but 6x6 instead of DxD and free of the lambda-only null-space directions that make the
-// primal fp32 solve lose ~1e-2 rad on 7/8-dof arms.  One step of iterative refinement with the residual formed
-// through J (not J J^T) recovers cond(J) instead of cond(J)^2 accuracy.
+// Pose-only LM step, one thread per waypoint (pose_step.cuh: pose_lm_update).
 template <class M>
 __global__ void __launch_bounds__(128)
 lm_pose_step_kernel(const float* __restrict__ q, const float* __restrict__ target, int64_t n, int64_t n_targets,
@@ -160,77 +86,11 @@ lm_pose_step_kernel(const float* __restrict__ q, const float* __restrict__ targe
     if (i >= n) return;
     float x[D];
     load_q<M>(q, i, x);
-    JointSink<M> js;
-    Frame F;
-    fk_chain<M>(x, js, F);
     float tg[7];
     const float* tp = target + (i % n_targets) * 7;
 #pragma unroll
     for (int k = 0; k < 7; ++k) tg[k] = __ldg(tp + k);
-    float e[6];
-    pose_error(tg, F, e);
-    float J[6][D];
-    geometric_jacobian<M>(js, F, J);
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        e[r] *= alpha_rot;
-        e[r + 3] *= alpha_pos;
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            J[r][d] *= alpha_rot;
-            J[r + 3][d] *= alpha_pos;
-        }
-    }
-    if (J_out) {
-        float* o = J_out + i * 6 * D;
-#pragma unroll
-        for (int r = 0; r < 6; ++r)
-#pragma unroll
-            for (int d = 0; d < D; ++d) o[r * D + d] = J[r][d];
-    }
-    if (e_out) {
-#pragma unroll
-        for (int r = 0; r < 6; ++r) e_out[i * 6 + r] = e[r];
-    }
-    float A[6][6], dinv[6];
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-        for (int c = 0; c <= r; ++c) {
-            float s = (r == c) ? lambda : 0.f;
-#pragma unroll
-            for (int d = 0; d < D; ++d) s = fmaf(J[r][d], J[c][d], s);
-            A[r][c] = s;
-        }
-    chol_lower<6>(A, dinv);
-    float z[6];
-    chol_solve<6>(A, dinv, e, z);
-    float dx[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-        float s = 0.f;
-#pragma unroll
-        for (int r = 0; r < 6; ++r) s = fmaf(J[r][d], z[r], s);
-        dx[d] = s;
-    }
-    // refinement: rho = e - J dx - lambda z
-    float rho[6], dz[6];
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-        float s = fmaf(-lambda, z[r], e[r]);
-#pragma unroll
-        for (int d = 0; d < D; ++d) s = fmaf(-J[r][d], dx[d], s);
-        rho[r] = s;
-    }
-    chol_solve<6>(A, dinv, rho, dz);
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-        float s = dx[d];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) s = fmaf(J[r][d], dz[r], s);
-        x[d] += s;
-    }
-    if (do_clamp) clamp_limits<M>(x);
+    pose_lm_update<M>(x, tg, alpha_pos, alpha_rot, lambda, do_clamp, J_out, e_out, i);
     store_q<M>(x_out, i, x);
 }
 

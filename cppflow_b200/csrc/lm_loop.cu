@@ -11,6 +11,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -68,6 +69,7 @@ struct LoopState {
     double last_tl = 0.0;
     std::chrono::steady_clock::time_point t0;
     float tag = 0.f;               // completion tag of the iteration in flight (i + 1)
+    bool fuse_pose = std::getenv("CPPFLOW_LM_NO_FUSE") == nullptr;  // pose step + metrics in one launch
     float* metrics_dst = nullptr;  // where the metrics kernel writes: the pinned host buffer itself when the device can
     bool zero_copy = false;        // address it (no copy engine round trip per iteration), the device scratch otherwise
 
@@ -106,12 +108,22 @@ struct LoopState {
 
     int launch() {
         const cppflow_lm_loop_job* j = job;
+        tag = (float)(i + 1);
+        if (zero_copy) *reinterpret_cast<volatile float*>(j->h_pinned_metrics + 7) = 0.f;  // not this iteration's tag
+        bool metrics_done = false;
         if (pose_pos_valid && pose_rot_valid) {
             // virtual configs = the current iterate (:253): their residual is identically zero -> d_xv = NULL
             if (int rc = cppflow_lm_full_step(j->robot, j->params_diff, x_cur, nullptr, j->d_target, 1, j->T, j->h_cuboids,
                                               j->h_Tcuboids, j->n_obstacles, CPPFLOW_LM_CLAMP, lm_ws, lm_ws_bytes, x_new, j->stream))
                 return rc;
             was_differencing = true;
+        } else if (fuse_pose && j->T <= 1024) {
+            // pose-only step and the metrics of its result in ONE launch (both kernels are launch-bound for one path)
+            if (int rc = pose_step_metrics_tagged(j->robot, j->params_pose, x_cur, j->d_target, j->T, j->h_cuboids, j->h_Tcuboids,
+                                                  j->n_obstacles, x_new, metrics_dst, tag, j->stream))
+                return rc;
+            was_differencing = false;
+            metrics_done = true;
         } else {
             if (int rc = cppflow_lm_pose_step(j->robot, j->params_pose, x_cur, j->d_target, j->T, j->T, 1, x_new, nullptr, nullptr, j->stream))
                 return rc;
@@ -119,11 +131,10 @@ struct LoopState {
         }
         if (n_sched < CPPFLOW_LM_SCHEDULE_MAX - 1) j->result->schedule[n_sched++] = was_differencing ? 'd' : 'p';
         float* tmp = x_cur; x_cur = x_new; x_new = tmp;  // clamp_to_joint_limits is fused into both steps (:259)
-        tag = (float)(i + 1);
-        if (zero_copy) *reinterpret_cast<volatile float*>(j->h_pinned_metrics + 7) = 0.f;  // not this iteration's tag
-        if (int rc = path_metrics_tagged(j->robot, x_cur, j->d_target, 1, j->T, j->h_cuboids, j->h_Tcuboids, j->n_obstacles,
-                                         metrics_dst, tag, j->stream))
-            return rc;
+        if (!metrics_done)
+            if (int rc = path_metrics_tagged(j->robot, x_cur, j->d_target, 1, j->T, j->h_cuboids, j->h_Tcuboids, j->n_obstacles,
+                                             metrics_dst, tag, j->stream))
+                return rc;
         if (!zero_copy) {
             cudaError_t e = cudaMemcpyAsync(j->h_pinned_metrics, d_metrics, 8 * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)j->stream);
             if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "lm_alternating_loss: %s", cudaGetErrorString(e));
