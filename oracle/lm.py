@@ -292,3 +292,99 @@ def path_metrics(model: RobotModel, x: torch.Tensor, target_path: torch.Tensor, 
     else:
         out["min_env"] = torch.tensor(float("inf"), dtype=x.dtype)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the alternating loop (optimization.py:147-373) and the validity check it calls (optimization_utils.py:836-923)
+
+
+def errors_are_below_threshold(constraints, error_t_cm, error_R_deg, qdeltas_revolute_deg, qdeltas_prismatic_cm):
+    """evaluation_utils.py:29-75: strict '<' on the maxima.  `constraints` = (max_allowed_position_error_cm,
+    max_allowed_rotation_error_deg, max_allowed_mjac_deg, max_allowed_mjac_cm)."""
+    pos_cm, rot_deg, mjac_deg, mjac_cm = constraints
+    pose_pos_valid = bool(error_t_cm.max() < pos_cm)
+    pose_rot_valid = bool(error_R_deg.max() < rot_deg)
+    mjac_rev_valid = bool(qdeltas_revolute_deg.abs().max() < mjac_deg)
+    mjac_pris_valid = bool(qdeltas_prismatic_cm.abs().max() < mjac_cm) if qdeltas_prismatic_cm.numel() > 0 else True
+    return (pose_pos_valid and pose_rot_valid and mjac_rev_valid and mjac_pris_valid,
+            (pose_pos_valid, pose_rot_valid, mjac_rev_valid, mjac_pris_valid))
+
+
+def x_is_valid(model: RobotModel, constraints, target_path: torch.Tensor, x: torch.Tensor, Tcuboids=None, cuboids=None):
+    """optimization_utils.py:836-923 for parallel_count == 1.  The klampt mesh checks of :889-900 (one
+    `config_self_collides` / `config_collides_with_env` query per configuration, collision_detection.py:89-120) are
+    answered by the capsule distances: a configuration collides when any capsule distance is negative - the check the
+    CUDA loop performs.  -> (x or None, (pose_pos_valid, pose_rot_valid, mjac_rev_valid, mjac_pris_valid,
+    is_a_self_collision, is_a_env_collision))"""
+    error_t_cm, error_R_deg = calculate_pose_error_cm_deg(model, x, target_path)
+    revolute_diffs_deg = torch.rad2deg(angular_changes(x[:, model.revolute_joint_idxs]))
+    prismatic_diffs_cm = 100 * prismatic_changes(x[:, model.prismatic_joint_idxs])
+    all_valid, flags = errors_are_below_threshold(constraints, error_t_cm, error_R_deg, revolute_diffs_deg,
+                                                  prismatic_diffs_cm)
+    is_a_self_collision = None
+    is_a_env_collision = None
+    if not all_valid:
+        return None, (*flags, is_a_self_collision, is_a_env_collision)
+    is_a_self_collision = bool((G.self_collision_distances(model, x).min(dim=1).values < 0).any())
+    if is_a_self_collision:
+        return None, (*flags, is_a_self_collision, is_a_env_collision)
+    is_a_env_collision = False
+    for Tc, c in zip(Tcuboids or [], cuboids or []):
+        if bool((G.env_collision_distances(model, x, c, Tc).min(dim=1).values < 0).any()):
+            is_a_env_collision = True
+    if is_a_env_collision:
+        return None, (*flags, is_a_self_collision, is_a_env_collision)
+    return x, (*flags, is_a_self_collision, is_a_env_collision)
+
+
+def run_lm_alternating_loss(model: RobotModel, x_seed: torch.Tensor, target_path: torch.Tensor, constraints,
+                            max_n_steps: int, return_if_valid_after_n_steps: int, convergence_threshold: float,
+                            Tcuboids=None, cuboids=None, params_diff: LmParams = ALT_LOSS_V2_1_DIFF,
+                            params_pose: LmParams = ALT_LOSS_V2_1_POSE):
+    """optimization.py:147-373 for ONE path, without the wall-clock exit (tmax_sec = infinity).
+    -> (x_opt, n_steps_taken, is_valid, schedule) with schedule[i] = 'p' (levenberg_marquardt_only_pose, :258) or
+    'd' (levenberg_marquardt_full with virtual_configs = x.clone(), :253-255) for iteration i."""
+
+    def calc_TL(qpath):  # :173-175
+        return float(angular_changes(qpath[:, model.revolute_joint_idxs]).abs().sum())
+
+    x = x_seed.clone()
+    tls_post_differencing = []
+    last_valid = None
+    last_valid_idx = -1
+    pose_pos_valid, pose_rot_valid = True, False  # :219-220: the first step is pose-only
+    converged = False
+    schedule = ""
+    i = 0
+    for i in range(max_n_steps):  # :230
+        took_differencing = pose_pos_valid and pose_rot_valid
+        if took_differencing:  # :251-255
+            pms = replace(params_diff, virtual_configs=x.clone())
+            x_new = levenberg_marquardt_full(model, x, target_path, pms, Tcuboids, cuboids)
+            schedule += "d"
+        else:  # :258
+            x_new = levenberg_marquardt_only_pose(model, x, target_path, params_pose)
+            schedule += "p"
+        x = clamp_to_joint_limits(model, x_new)  # :259
+        tl_new = calc_TL(x)  # :268
+        if took_differencing:  # :275-297
+            if not converged and len(tls_post_differencing) > 0:
+                if abs(tl_new - tls_post_differencing[-1]) < convergence_threshold:
+                    converged = True
+                    if last_valid_idx == i - 1:
+                        break
+            tls_post_differencing.append(tl_new)
+        x_sol, (pose_pos_valid, pose_rot_valid, _, _, _, _) = x_is_valid(model, constraints, target_path, x, Tcuboids,
+                                                                         cuboids)  # :318
+        if x_sol is not None:  # :326-335
+            last_valid_idx = i
+            last_valid = x.clone()
+            if converged:
+                break
+        if last_valid is not None:  # :346-358
+            if i > return_if_valid_after_n_steps:
+                break
+            if i > max_n_steps:
+                break
+    x_return = last_valid if last_valid is not None else x
+    return x_return, i, last_valid is not None, schedule

@@ -53,10 +53,14 @@ def angular_subtraction(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 def geodesic_distance_between_quaternions(q1: torch.Tensor, q2: torch.Tensor) -> torch.Tensor:
-    """Quoted by the reference at data_types.py:408-411 (acos clamp epsilon 1e-7)."""
+    """The first two lines are quoted by the reference at data_types.py:408-411 (acos clamp epsilon 1e-7).  jrl then
+    folds the angle into [0, pi] (`abs(remainder(d + pi, 2 pi) - pi)`), which makes q and -q the same rotation:
+    2 acos(dot) -> 2 acos(|dot|).  Without it a target quaternion stored with the opposite sign (the csv target paths
+    carry arbitrary signs) would read as a 360 degree error and no plan could ever be valid."""
     acos_clamp_epsilon = 1e-7
     dot = torch.clip(torch.sum(q1 * q2, dim=1), -1, 1)
-    return 2 * torch.acos(torch.clamp(dot, -1 + acos_clamp_epsilon, 1 - acos_clamp_epsilon))
+    distance = 2 * torch.acos(torch.clamp(dot, -1 + acos_clamp_epsilon, 1 - acos_clamp_epsilon))
+    return torch.abs(torch.remainder(distance + torch.pi, 2 * torch.pi) - torch.pi)
 
 
 def rpy_to_rotation_matrix(rpy, dtype=torch.float64) -> torch.Tensor:

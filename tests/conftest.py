@@ -17,3 +17,10 @@ def golden():
     import numpy as np
 
     return np.load(os.path.join(REPO, "tests", "golden", "reference_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def loop_golden():
+    import numpy as np
+
+    return np.load(os.path.join(REPO, "tests", "golden", "reference_loop_golden.npz"))

@@ -231,3 +231,43 @@ def test_batched_equals_per_path_collision_flags(golden):
 def test_geodesic_floor():
     q = T([[1.0, 0, 0, 0]], torch.float64)
     assert abs(geodesic_distance_between_quaternions(q, q).item() - 2 * math.acos(1 - 1e-7)) < 1e-9
+
+
+def test_geodesic_distance_is_sign_invariant():
+    """q and -q are the same rotation (jrl folds 2 acos(dot) into [0, pi])."""
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn((50, 4), generator=g, dtype=torch.float64)
+    b = torch.randn((50, 4), generator=g, dtype=torch.float64)
+    a, b = a / a.norm(dim=1, keepdim=True), b / b.norm(dim=1, keepdim=True)
+    d = geodesic_distance_between_quaternions(a, b)
+    assert torch.allclose(d, geodesic_distance_between_quaternions(a, -b), atol=1e-6)
+    assert (d >= 0).all() and (d <= math.pi + 1e-9).all()
+
+
+LOOP_PATTERNS = {  # planners.py:402-422
+    "normal": dict(max_n_steps=20, return_if_valid_after_n_steps=0, convergence_threshold=1e6),
+    "anytime": dict(max_n_steps=75, return_if_valid_after_n_steps=int(1e8), convergence_threshold=0.005),
+}
+LOOP_CASES = ["fetch_smooth", "fetch_noisy", "fetch_arm_smooth", "panda_smooth", "panda_noisy", "fetch_colliding"]
+
+
+@pytest.mark.parametrize("case", LOOP_CASES)
+@pytest.mark.parametrize("dt_name", ["f32", "f64"])
+def test_alternating_loop_matches_reference_loop(loop_golden, case, dt_name):
+    """oracle.lm.run_lm_alternating_loss == the reference's own run_lm_optimization / run_lm_alternating_loss
+    (optimization.py:147-426, run by tests/golden/make_golden_loop.py): same step sequence, n_steps_taken, is_valid
+    and returned iterate, in the reference's float32 and in float64, for both of the planner's call patterns."""
+    g = loop_golden
+    dt = torch.float32 if dt_name == "f32" else torch.float64
+    m = R.get_model(str(g[f"{case}/robot"]))
+    cuboids = [T(c, dt) for c in g[f"{case}/cuboids"]]
+    Tcuboids = [T(t, dt) for t in g[f"{case}/Tcuboids"]]
+    for pat, kw in LOOP_PATTERNS.items():
+        key = f"{case}/{pat}/{dt_name}"
+        x, n, valid, sched = L.run_lm_alternating_loss(m, T(g[f"{case}/x_seed"], dt), T(g[f"{case}/target"], dt),
+                                                       (0.01, 0.1, 7.0, 2.0), Tcuboids=Tcuboids, cuboids=cuboids, **kw)
+        assert sched == str(g[f"{key}/schedule"]), key
+        assert n == int(g[f"{key}/n_steps_taken"]) and valid == bool(g[f"{key}/is_valid"]), key
+        np.testing.assert_allclose(x.numpy(), g[f"{key}/x_opt"], atol=1e-6 if dt_name == "f32" else 1e-12)
+    # the golden set covers: valid after the first pose steps, convergence exit, never valid
+    assert bool(g["fetch_smooth/normal/f32/is_valid"]) and not bool(g["fetch_colliding/anytime/f32/is_valid"])
