@@ -10,7 +10,10 @@ with every residual term on (pose + joint differencing + virtual configs + capsu
 by clamp_to_joint_limits, over all P*T waypoints; one waypoint evaluation = FK + 6xD Jacobian + 28 capsule-pair and
 40 capsule-cuboid distances + its share of the block-tridiagonal normal-equation assembly and solve.
 Multi-GPU: weak scaling - every rank refines its own shard of P paths, no collective in the data path; after the
-timed steps the per-path costs are all-gathered over NCCL and the argmin taken (inside the timed region).
+timed steps every rank reduces its per-path costs to one packed key on the device and the keys are all-gathered over
+NCCL (inside the timed region; the host reads the result after the closing event).  Extra keys of the same line:
+`strong` (the SAME 8192 paths split P/N per GPU), `quality` (the reference's alternating step sequence on a
+collision-free variant of the workload, cost argmin over valid paths), per-kernel times and roofline fractions.
 """
 import argparse
 import json
@@ -30,12 +33,15 @@ F_ASSEMBLE = 581 + 96 + 90 + 624 + 2520 + 4800 + 63  # FK, Jacobian, pose error,
 F_SOLVE = 1451                                       # block-tridiagonal factor/solve share: (7/3) D^3 + 4 D^2
 F_STEP_SURVEY = 9100                                 # the per-eval figure SURVEY.md 8d quotes for the fused iteration
 BYTES_PER_EVAL = 64                                  # read q once, write x_new once (8 dof * 4 B * 2)
+F_POSE_STEP = 581 + 96 + 90 + 624 + 315              # pose-only LM step: FK, Jacobian, error, normal equations, D x D solve
+F_FLAGS = 581 + 63 + 2520 + 4800                     # collision flags: all-link FK + 28 pair + 40 capsule-cuboid distances
+SOLVE_WS_PASSES = 3                                  # block solve: read A, write (-S^-1, u), read them back
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=20, help="timed LM iterations (20 = the reference's max_n_steps, planners.py:416)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--paths", type=int, default=8192)
@@ -138,8 +144,10 @@ def cpu_reference_step_rate(T: int, sample_paths: int, steps: int, warmup: int):
 def run_reference(args, rank: int):
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    warmup = 1 if args.warmup > 0 else 0
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    # a step of the reference arm is a bounded sample of the workload: sized so that steps + warmup end within minutes
+    budget_paths = int(max(2, min(args.cpu_sample_paths, 600.0 / (0.065 * (steps + warmup)))))
+    args.cpu_sample_paths = budget_paths
     rate, dt, cores = cpu_reference_step_rate(args.waypoints, args.cpu_sample_paths, steps, warmup)
     sample = (f"{args.cpu_sample_paths} of {args.paths} paths x {args.waypoints} waypoints per step (dense get_r_and_J + "
               f"_lm_full_step, all terms on), fp32, torch {torch.__version__}, {cores} threads; evals/s is size-independent "
@@ -292,6 +300,24 @@ def emit(line: dict):
 _REAL_STDOUT = 1
 
 
+def time_pipeline(rpipe, x_in, x_out, steps, barrier, metrics=None, tail=None):
+    """K pipelined steps (+ optionally each chunk's metrics and a tail enqueued on the current stream) between two CUDA
+    events with a barrier + device synchronisation on both sides.  -> (ms total, whatever `tail` returned)"""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    rpipe.begin()
+    for _ in range(steps):
+        rpipe.enqueue_step(x_in, x_out)
+    if metrics is not None:
+        rpipe.enqueue_metrics(x_out, metrics)
+    rpipe.end()
+    pending = tail() if tail is not None else None
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1), pending
+
+
 def main():
     global _REAL_STDOUT
     args = parse()
@@ -318,17 +344,16 @@ def main():
 
     from cppflow_b200 import ops, _lib
     from cppflow_b200.robot import get_robot
-    from cppflow_b200.synthetic import synthetic_problem, synthetic_seeds_host
-    from cppflow_b200.lm_hyper_parameters import all_terms_parameters
-    from cppflow_b200.distributed import gather_costs_and_argmin
+    from cppflow_b200.synthetic import synthetic_problem, synthetic_seeds_host, FEASIBLE
+    from cppflow_b200.lm_hyper_parameters import all_terms_parameters, ALT_LOSS_V2_1_DIFF, ALT_LOSS_V2_1_POSE
+    from cppflow_b200.distributed import enqueue_argmin, shard_range
+    from cppflow_b200.pipeline import ResidentPipeline, HostPipeline, numa_local
     import ctypes
 
     lib = _lib.load()
     robot = get_robot("fetch")
     P, T, D = args.paths, args.waypoints, robot.ndof
     problem = synthetic_problem(robot, T, seed=0, device=dev)
-    from cppflow_b200.pipeline import numa_local
-
     with numa_local(dev):  # page-locked buffers on the GPU's own NUMA node
         _, x_host = synthetic_seeds_host(robot, P, T, seed=0, shard=rank, pin=True)
     x0 = x_host.to(dev)
@@ -337,69 +362,83 @@ def main():
     ob = problem.obstacle_tables
     rid = robot.robot_id
     evals_per_step = P * T
+    steps, warmup = args.steps, max(args.warmup, 3)
 
     def step(src=x0, dst=x_out):
         return ops.lm_full_step(rid, D, prm, src, None, problem.target_path, P, T, ob, True, out=dst)
-
-    # the K timed iterations run chunk-pipelined: the path set is cut into `--chunks` chunks with one stream each, and
-    # the block solve of one chunk runs under the assembly of another (pipeline.ResidentPipeline, CPPFLOW_LM_OVERLAP)
-    from cppflow_b200.pipeline import ResidentPipeline
-
-    rpipe = ResidentPipeline(problem, P, all_terms_parameters(), n_chunks=args.chunks)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    rpipe.begin()
-    for _ in range(max(args.warmup, 3)):
-        rpipe.enqueue_step(x0, x_out)
-    rpipe.end()
-    # warm up the once-per-job tail too (path metrics kernel, NCCL gather, torch argmin): first calls load modules
-    gather_costs_and_argmin(ops.path_metrics(rid, D, x_out, problem.target_path, P, T, ob), problem.constraints, rank, world)
-    barrier()
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
 
-    # ---- headline: K steps, inputs resident in HBM, CUDA events, max over ranks
-    sampler = ClockSampler(physical_gpu_index(local_rank), period=float(os.environ.get("BENCH_CLOCK_PERIOD", "0.01")))
+    # the K timed iterations run chunk-pipelined: the path set is cut into `--chunks` chunks with one stream each, and
+    # the block solve of one chunk runs under the assembly of another (pipeline.ResidentPipeline, CPPFLOW_LM_OVERLAP)
+    rpipe = ResidentPipeline(problem, P, all_terms_parameters(), n_chunks=args.chunks)
+    metrics = torch.empty((P, 8), device=dev, dtype=torch.float32)
+
+    def argmin_tail():
+        # every rank: packed (invalid, TL, global index) key of its best path -> ONE all-gather of 3 int64 per rank
+        return enqueue_argmin(metrics, problem.constraints, rank * P, world)
+
+    for _ in range(warmup):
+        step()
+    # warm-up of the pipelined steps AND of the once-per-job tail (metrics kernel, NCCL all-gather): first calls load modules
+    time_pipeline(rpipe, x0, x_out, warmup, barrier, metrics, argmin_tail)[1].result()
+
+    # ---- headline: K steps + the cost argmin, inputs resident in HBM, CUDA events, max over ranks
+    sampler = ClockSampler(physical_gpu_index(local_rank), period=float(os.environ.get("BENCH_CLOCK_PERIOD", "0.005")))
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    dbg = [] if os.environ.get("BENCH_DEBUG_EVENTS") else None
-    rpipe.begin()
-    for _ in range(args.steps):
-        rpipe.enqueue_step(x0, x_out)
-        if dbg is not None:
-            dbg.append(torch.cuda.Event(enable_timing=True))
-            dbg[-1].record()
-    rpipe.end()
-    if dbg is not None:
-        torch.cuda.synchronize(dev)
-        ts = [e0.elapsed_time(dbg[0])] + [dbg[i].elapsed_time(dbg[i + 1]) for i in range(len(dbg) - 1)]
-        print("per-step ms:", [round(t, 2) for t in ts[:12]], "...", [round(t, 2) for t in ts[-6:]], file=sys.stderr)
-    metrics = ops.path_metrics(rid, D, x_out, problem.target_path, P, T, ob)
-    best_cost, best_rank, best_idx = gather_costs_and_argmin(metrics, problem.constraints, rank, world)
-    e1.record()
-    barrier()
+    ms_total, pending = time_pipeline(rpipe, x0, x_out, steps, barrier, metrics, argmin_tail)
+    # a 20-step region is ~10 ms: keep the sampler running over a few more identical regions so that it sees load
+    for _ in range(3):
+        time_pipeline(rpipe, x0, x_out, steps, barrier, metrics, argmin_tail)
     clocks = sampler.stop()
-    ms_total = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_per_step = ms_total / args.steps
+    best = pending.result()
+    ms_total = max_over_ranks(ms_total)
+    ms_per_step = ms_total / steps
     value = world * evals_per_step / (ms_per_step * 1e-3)
+    # the same K steps without the tail: what the tail costs
+    ms_steps_only = max_over_ranks(time_pipeline(rpipe, x0, x_out, steps, barrier)[0]) / steps
+
+    # ---- strong scaling: the SAME P paths split over the ranks (P / N per GPU), K steps, no tail
+    strong = None
+    sizes = sorted({max(16, P // n) for n in (2, 4, 8)} | ({max(16, P // world)} if world > 1 else set()), reverse=True)
+    per_size = {}
+    for n_paths in sizes:
+        s0, _ = shard_range(P, rank % max(1, P // n_paths), max(1, P // n_paths))
+        xs = x0[s0 * T:(s0 + n_paths) * T]
+        pipe_s = ResidentPipeline(problem, n_paths, all_terms_parameters(), n_chunks=args.chunks)
+        time_pipeline(pipe_s, xs, x_out[: n_paths * T], warmup, barrier)
+        per_size[n_paths] = max_over_ranks(time_pipeline(pipe_s, xs, x_out[: n_paths * T], steps, barrier)[0]) / steps
+        del pipe_s
+    if world > 1:
+        ms_strong = per_size[max(16, P // world)]
+        strong = {"paths_total": P, "paths_per_gpu": max(16, P // world), "ms_per_step": ms_strong,
+                  "evals_per_s": evals_per_step / (ms_strong * 1e-3),
+                  "efficiency": ms_steps_only / (world * ms_strong),
+                  "what": "same 8192 x 300 workload split P/N per GPU, K pipelined steps, max over ranks; efficiency = "
+                          "t(P paths on one GPU, measured in this run) / (N * t(P/N paths per GPU))"}
+    strong_preview = {
+        "what": "per-GPU step time with P/n paths resident (paths are independent and no data-path collective exists, so "
+                "this is the n-GPU strong-scaling step time); efficiency = t(P) / (n * t(P/n))",
+        "ms_per_step": {str(n): per_size[n] for n in sizes},
+        "efficiency": {f"1/{P // n}": ms_steps_only / ((P // n) * per_size[n]) for n in sizes},
+    }
 
     # ---- e2e: host buffers in, host buffers out, through the public API, copies inside the timed region
-    from cppflow_b200.pipeline import HostPipeline
-
     pipe = HostPipeline(problem, P, all_terms_parameters())
     with numa_local(dev):
         out_host = torch.empty_like(x_host).pin_memory()
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(steps, 20))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(2):
         pipe.refine(x_host, out_host)
     barrier()
@@ -410,17 +449,13 @@ def main():
     e1.record()
     barrier()
     wall = time.perf_counter() - t0
-    e2e_ms = max(e0.elapsed_time(e1), 0.0)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
     e2e_value = world * evals_per_step / (e2e_ms / e2e_steps * 1e-3)
     h2d = x_host.numel() * 4
     d2h = out_host.numel() * 4
 
     # ---- the same iteration on ONE stream (assembly and solve back to back), for comparison
-    n_single = max(5, min(args.steps, 100))
+    n_single = max(5, min(steps, 100))
     barrier()
     e0.record()
     for _ in range(n_single):
@@ -430,7 +465,7 @@ def main():
     ms_single = e0.elapsed_time(e1) / n_single
 
     # ---- per-kernel durations (live, CUDA events on the launching stream) for the roofline
-    n_prof = max(5, min(args.steps, 50))
+    n_prof = max(5, min(steps, 50))
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_prof)]
     ws = ops._workspace(dev, lib.cppflow_lm_full_workspace_bytes(rid, P, T), "lm_full")
     cu, tc, no = ops._obs(ob)
@@ -445,6 +480,24 @@ def main():
     torch.cuda.synchronize(dev)
     ms_assemble = statistics.mean(ev[i][0].elapsed_time(ev[i][1]) for i in range(n_prof))
     ms_solve = statistics.mean(ev[i][1].elapsed_time(ev[i][2]) for i in range(n_prof))
+
+    def timed(fn, reps=10):
+        fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / reps
+
+    # the other kernels of the path at the headline size (8192 x 300 configurations each)
+    prm_pose, prm_diff = ops.make_params(ALT_LOSS_V2_1_POSE), ops.make_params(ALT_LOSS_V2_1_DIFF)
+    ms_pose = timed(lambda: ops.lm_pose_step(rid, D, prm_pose, x0, problem.target_path, True, out=x_out))
+    ms_flags = timed(lambda: ops.collision_flags(rid, D, x0, ob))
+    ms_metrics = timed(lambda: ops.path_metrics(rid, D, x0, problem.target_path, P, T, ob))
+    ms_diff = timed(lambda: ops.lm_full_step(rid, D, prm_diff, x0, None, problem.target_path, P, T, ob, True, out=x_out))
 
     # ---- FP32 peak measured live (MEASURED_PEAKS.json has no FP32 entry)
     scratch = torch.zeros(16, device=dev)
@@ -490,9 +543,9 @@ def main():
         "ms_per_launch": ms_assemble,
         "traffic": (traffic or {}).get("lm_assemble_kernel"),
     }
-    solve_bytes = 3 * ws_bytes + 2 * x0.numel() * 4  # read blocks, write (S^-1,u), read them back; read q, write x
+    solve_bytes = SOLVE_WS_PASSES * ws_bytes + 2 * x0.numel() * 4  # block passes over the workspace; read q, write x
     roofline_solve = {
-        "kernel": "lm_block_solve_kernel<Fetch> (twisted block-Thomas sweep, two lanes per path, TMA bulk-copy block loads)",
+        "kernel": "lm_block_solve_kernel<Fetch> (twisted block-Thomas sweep, TMA bulk-copy block loads)",
         "bound": "hbm",
         "achieved": solve_bytes / (ms_solve * 1e-3) / 1e9,
         "peak": hbm_peak,
@@ -505,20 +558,67 @@ def main():
     }
     step_tflops = F_STEP_SURVEY * evals_per_step / (ms_per_step * 1e-3) / 1e12
     roofline_step = {
-        "what": "whole fused iteration, SURVEY 8d figure of 9.1 kFLOP per evaluation",
+        "what": "whole fused iteration (the K timed steps INCLUDING the cost-argmin tail), SURVEY 8d figure of 9.1 kFLOP per evaluation",
         "bound": "fp32", "achieved": step_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
         "frac": step_tflops / fp32_peak_tflops,
+        "frac_steps_only": F_STEP_SURVEY * evals_per_step / (ms_steps_only * 1e-3) / 1e12 / fp32_peak_tflops,
         "hbm_algorithmic_gbs": BYTES_PER_EVAL * evals_per_step / (ms_per_step * 1e-3) / 1e9,
         "hbm_peak_gbs": hbm_peak,
     }
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    def frac_fp32(flop_per_eval, ms):
+        return flop_per_eval * evals_per_step / (ms * 1e-3) / 1e12 / fp32_peak_tflops
 
-    # the extra keys below must never cost the headline its line: a failure is reported in place
+    rooflines_other = {
+        "lm_pose_step_kernel": {"bound": "fp32", "flop_per_eval": F_POSE_STEP, "ms_per_launch": ms_pose,
+                                "frac": frac_fp32(F_POSE_STEP, ms_pose),
+                                "hbm_frac": BYTES_PER_EVAL * evals_per_step / (ms_pose * 1e-3) / 1e9 / hbm_peak},
+        "collision_flags_kernel": {"bound": "fp32", "flop_per_eval": F_FLAGS, "ms_per_launch": ms_flags,
+                                   "frac": frac_fp32(F_FLAGS, ms_flags)},
+        "path_metrics_kernel": {"bound": "fp32", "flop_per_eval": F_FLAGS + 90, "ms_per_launch": ms_metrics,
+                                "frac": frac_fp32(F_FLAGS + 90, ms_metrics)},
+        "differencing_step (assemble + solve, ALT_LOSS_V2_1_DIFF)": {"ms_per_step": ms_diff},
+    }
+
+    # ---- quality: the reference's alternating step sequence on the collision-free variant of the workload; the cost
+    # argmin then has valid paths to choose from (the headline workload's target path runs through a cuboid)
+    def quality():
+        sched = "pppddppdppp"
+        prob_f = synthetic_problem(robot, T, device=dev, **FEASIBLE)
+        _, xf_host = synthetic_seeds_host(robot, P, T, shard=rank, **FEASIBLE)
+        xf = xf_host.to(dev)
+        bufs = [torch.empty_like(xf), torch.empty_like(xf)]
+        mq = torch.empty((P, 8), device=dev, dtype=torch.float32)
+
+        def run():
+            src = xf
+            for i, c in enumerate(sched):
+                dst = bufs[i % 2]
+                if c == "p":
+                    ops.lm_pose_step(rid, D, prm_pose, src, prob_f.target_path, True, out=dst)
+                else:
+                    ops.lm_full_step(rid, D, prm_diff, src, None, prob_f.target_path, P, T, prob_f.obstacle_tables, True, out=dst)
+                src = dst
+            _lib.check(lib.cppflow_path_metrics(rid, _lib.ptr(src), _lib.ptr(prob_f.target_path), P, T,
+                                                *ops._obs(prob_f.obstacle_tables), _lib.ptr(mq), st))
+            return enqueue_argmin(mq, prob_f.constraints, rank * P, world)
+
+        run().result()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        pend = run()
+        b.record()
+        barrier()
+        ms = max_over_ranks(a.elapsed_time(b))
+        bq = pend.result()
+        assert bq.valid and bq.cost < 1e9, f"no valid path after {sched}: best cost {bq.cost}"
+        return {"schedule": sched, "workload": f"same shape, collision-free reference path (seed {FEASIBLE['seed']}, amplitude {FEASIBLE['amp']})",
+                "ms_total": ms, "evals_per_s": world * evals_per_step * len(sched) / (ms * 1e-3),
+                "n_valid": bq.n_valid, "n_paths": world * P, "best_cost": bq.cost, "best_rank": bq.rank, "best_path": bq.index}
+
     def guarded(fn, *a, **kw):
+        # the extra keys below must never cost the headline its line: a failure is reported in place
         try:
             return fn(*a, **kw)
         except Exception as e:  # noqa: BLE001
@@ -527,8 +627,16 @@ def main():
             traceback.print_exc(file=sys.stderr)
             return {"error": f"{type(e).__name__}: {e}"}
 
+    quality_res = guarded(quality) if world == 1 else quality()  # collective inside: every rank must take part
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     plan = None
     plan_all = None
+    dp_ms = None
     if world == 1:
         plan_all = guarded(plan_all_problems_gpu, dev)
         got = guarded(plan_latency_gpu, dev)
@@ -536,6 +644,22 @@ def main():
             plan, plan_problem, plan_qs = got
             if not args.no_cpu_baseline:
                 plan["cpu_baseline"] = guarded(plan_latency_cpu, plan_problem, plan_qs, plan["schedule"])
+
+            def dp_times():
+                out = {}
+                from cppflow_b200.collision_detection import qpaths_batched_collisions
+                from cppflow_b200.planners import LmIkCandidateGenerator
+
+                for k in (175, 300):
+                    qs = plan_qs.to(dev) if k == 175 else LmIkCandidateGenerator(seed=2)(plan_problem, k).contiguous()
+                    sv, evf = qpaths_batched_collisions(plan_problem, qs)
+                    ms = timed(lambda: ops.dp_search(rid, D, qs, sv, evf))
+                    n_t = qs.shape[1]
+                    out[f"k{k}"] = {"ms": ms, "us_per_step": ms * 1e3 / (n_t - 1), "waypoints": n_t,
+                                    "flags_ms": timed(lambda: qpaths_batched_collisions(plan_problem, qs))}
+                return out
+
+            dp_ms = guarded(dp_times)
         else:
             plan = got
 
@@ -554,8 +678,8 @@ def main():
         "value": value,
         "unit": "waypoint-evals/s",
         "n_gpus": world,
-        "steps": args.steps,
-        "warmup": max(args.warmup, 3),
+        "steps": steps,
+        "warmup": warmup,
         "ms_per_step": ms_per_step,
         "higher_is_better": True,
         "scaling": "weak",
@@ -567,16 +691,25 @@ def main():
         "e2e": {"value": e2e_value, "unit": "waypoint-evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": wall / e2e_steps * 1e3, "steps": e2e_steps,
                 "api": "cppflow_b200.pipeline.HostPipeline.refine(host x -> host x_new), pinned host buffers"},
-        "gpu_launches": args.steps * 2 * len(rpipe.chunks) + 1,
+        "gpu_launches": steps * 2 * len(rpipe.chunks) + len(rpipe.chunks),
+        "ms_per_step_without_tail": ms_steps_only,
         "single_stream_ms_per_step": ms_single,
         "roofline": roofline,
         "roofline_solve": roofline_solve,
         "roofline_step": roofline_step,
-        "kernel_ms": {"lm_assemble_kernel": ms_assemble, "lm_block_solve_kernel": ms_solve},
+        "rooflines_other": rooflines_other,
+        "kernel_ms": {"lm_assemble_kernel": ms_assemble, "lm_block_solve_kernel": ms_solve, "lm_pose_step_kernel": ms_pose,
+                      "collision_flags_kernel": ms_flags, "path_metrics_kernel": ms_metrics, "dp_search": dp_ms},
+        "strong": strong,
+        "strong_preview": strong_preview,
+        "quality": quality_res,
         "cpu_baseline": cpu_baseline,
         "plan_latency": plan,
         "plan_all_problems": plan_all,
-        "argmin": {"cost": best_cost, "rank": best_rank, "path": best_idx},
+        "argmin": {"cost": best.cost, "rank": best.rank, "path": best.index, "n_valid": best.n_valid,
+                   "trajectory_length": best.trajectory_length,
+                   "note": "headline workload: the reference joint path runs through a cuboid, so no path can be valid; "
+                           "invalid paths are ranked by trajectory length (see `quality` for the feasible variant)"},
     }
     emit(line)
     if world > 1:

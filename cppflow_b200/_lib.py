@@ -59,10 +59,10 @@ class ConstraintsC(C.Structure):
     """cppflow_constraints"""
 
     _fields_ = [
-        ("max_allowed_position_error_cm", C.c_float),
-        ("max_allowed_rotation_error_deg", C.c_float),
-        ("max_allowed_mjac_deg", C.c_float),
-        ("max_allowed_mjac_cm", C.c_float),
+        ("max_allowed_position_error_cm", C.c_double),
+        ("max_allowed_rotation_error_deg", C.c_double),
+        ("max_allowed_mjac_deg", C.c_double),
+        ("max_allowed_mjac_cm", C.c_double),
     ]
 
 
@@ -104,11 +104,14 @@ class LmLoopJobC(C.Structure):
     ]
 
 
+ABI_VERSION = 2  # CPPFLOW_ABI_VERSION of include/cppflow_b200.h
+
 _VP, _I, _I64, _SZ, _F, _DBL = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float, C.c_double
 _PROTOTYPES = {
     # name: (restype, argtypes)
     "cppflow_version": (C.c_char_p, []),
     "cppflow_last_error": (C.c_char_p, []),
+    "cppflow_abi_info": (_I, [C.POINTER(C.c_int64), _I]),
     "cppflow_robot_info_get": (_I, [_I, C.POINTER(RobotInfoC)]),
     "cppflow_forward_kinematics": (_I, [_I, _VP, _I64, _VP, _VP]),
     "cppflow_jacobian": (_I, [_I, _VP, _I64, _VP, _VP]),
@@ -154,18 +157,32 @@ def load(build_if_missing: bool = True):
         if build_if_missing and _build.is_stale():
             try:
                 _build.build()
-            except Exception as e:  # a prebuilt, possibly stale, library is still usable on a box without nvcc
-                if not os.path.exists(path):
+            except Exception as e:  # a prebuilt library is still usable on a box without nvcc - IF its ABI matches,
+                if not os.path.exists(path):  # which the check below establishes
                     raise RuntimeError(f"libcppflow_b200.so is missing and could not be built: {e}") from e
+                import warnings
+
+                warnings.warn(f"libcppflow_b200.so is older than its sources and could not be rebuilt ({e}); "
+                              "loading it after an ABI check")
         if not os.path.exists(path):
             raise RuntimeError(
                 f"{path} not found. Build it with `python -m cppflow_b200._build` (needs nvcc); there is no CPU fallback."
             )
         lib = C.CDLL(path)
+        missing = [name for name in _PROTOTYPES if not hasattr(lib, name)]
+        if missing:
+            raise RuntimeError(f"{path} does not export {missing}: it was built from another include/cppflow_b200.h; "
+                               "rebuild with `python -m cppflow_b200._build --force`")
         for name, (restype, argtypes) in _PROTOTYPES.items():
             fn = getattr(lib, name)
             fn.restype = restype
             fn.argtypes = argtypes
+        got = (C.c_int64 * 6)()
+        n = lib.cppflow_abi_info(got, 6)
+        want = [ABI_VERSION] + [C.sizeof(t) for t in (LmParamsC, RobotInfoC, ConstraintsC, LmLoopResultC, LmLoopJobC)]
+        if n != 6 or list(got) != want:
+            raise RuntimeError(f"{path}: ABI mismatch (library {list(got)[:n]}, binding {want}): struct layouts differ, "
+                               "refusing to call into it; rebuild with `python -m cppflow_b200._build --force`")
         _LIB = lib
         return lib
 

@@ -49,7 +49,15 @@ static void fill_info(cppflow_robot_info* out) {
 
 using namespace cppflow;
 
-extern "C" const char* cppflow_version(void) { return "cppflow_b200 0.1.0 (sm_100a)"; }
+extern "C" const char* cppflow_version(void) { return "cppflow_b200 0.2.0 (sm_100a)"; }
+
+extern "C" int cppflow_abi_info(int64_t* out, int n) {
+    const int64_t v[6] = {CPPFLOW_ABI_VERSION, (int64_t)sizeof(cppflow_lm_params), (int64_t)sizeof(cppflow_robot_info),
+                          (int64_t)sizeof(cppflow_constraints), (int64_t)sizeof(cppflow_lm_loop_result),
+                          (int64_t)sizeof(cppflow_lm_loop_job)};
+    for (int k = 0; out && k < n && k < 6; ++k) out[k] = v[k];
+    return 6;
+}
 
 extern "C" const char* cppflow_last_error(void) { return g_last_error; }
 

@@ -1,6 +1,7 @@
 // Shared host-side helpers for the C-ABI translation units.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 
@@ -67,5 +68,25 @@ int pose_step_metrics_tagged(int robot, const cppflow_lm_params* params, const f
                              float tag, void* stream);
 
 inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+// cudaFuncSetAttribute applies to the CURRENT device only: the opt-in to more than 48 KB of dynamic shared memory is
+// remembered per (kernel instantiation, device ordinal), not per process.  `granted` is a static of the calling
+// launch function; relaxed atomics make concurrent host threads at worst repeat the (idempotent) call.
+constexpr int CPPFLOW_MAX_DEVICES = 64;
+struct SmemGrant {
+    std::atomic<size_t> bytes[CPPFLOW_MAX_DEVICES];
+};
+template <class K>
+inline int ensure_dynamic_smem(K kernel, size_t bytes, SmemGrant& granted) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+    const bool tracked = dev >= 0 && dev < CPPFLOW_MAX_DEVICES;
+    if (tracked && granted.bytes[dev].load(std::memory_order_relaxed) >= bytes) return CPPFLOW_OK;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if (tracked) granted.bytes[dev].store(bytes, std::memory_order_relaxed);
+    return CPPFLOW_OK;
+}
 
 }  // namespace cppflow

@@ -282,6 +282,7 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
 
 struct SolveParams {
     float b_rev, b_pri;  // beta of revolute / prismatic dofs
+    float pivot_floor;   // lambda: every Schur complement of J^T J + lambda I has pivots >= lambda
     int do_clamp;
     unsigned zero;       // always 0; a run-time value so that dependency tokens built from it survive the optimisers
 };
@@ -514,7 +515,7 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
                     nS[tri(i, j)] = fmaf(bs.template bb<i, j>(), nS[tri(i, j)], blk[tri(i, j)]);
                 });
             });
-            sweep_neg_inverse<D>(nS, u);
+            sweep_neg_inverse<D>(nS, u, prm.pivot_floor);
         }
         // block t <- (-S_t^-1 packed, u_t) with 16-byte generic stores: a warp instruction covers 256 contiguous bytes
         // per side.  (An earlier version staged the block in shared memory and sent it with a TMA bulk store: the
@@ -582,7 +583,7 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
                 Sm[tri(i, j)] = fmaf(bs.template bb<i, j>(), nS[tri(i, j)] + so, blk[tri(i, j)]);
             });
         });
-        sweep_neg_inverse<D>(Sm, dx);  // both lanes of the pair compute dx_m
+        sweep_neg_inverse<D>(Sm, dx, prm.pivot_floor);  // both lanes of the pair compute dx_m
         if (side == 0 && active) {
             float xn[D];
 #pragma unroll
@@ -724,7 +725,7 @@ lm_block_solve_resident_kernel(const float* __restrict__ q, int64_t P, int64_t T
                 nS[tri(i, j)] = fmaf(bs.template bb<i, j>(), nS[tri(i, j)], blk[tri(i, j)]);
             });
         });
-        sweep_neg_inverse<D>(nS, u);
+        sweep_neg_inverse<D>(nS, u, prm.pivot_floor);
         float v[NW];
 #pragma unroll
         for (int i = 0; i < NT; ++i) v[i] = nS[i];
@@ -752,7 +753,7 @@ lm_block_solve_resident_kernel(const float* __restrict__ q, int64_t P, int64_t T
                 Sm[tri(i, j)] = fmaf(bs.template bb<i, j>(), nS[tri(i, j)] + so, blk[tri(i, j)]);
             });
         });
-        sweep_neg_inverse<D>(Sm, dx);
+        sweep_neg_inverse<D>(Sm, dx, prm.pivot_floor);
         if (side == 0) {
             float xn[D];
 #pragma unroll
@@ -820,6 +821,7 @@ static void make_params(const cppflow_lm_params* p, int n_obstacles, int do_clam
     ap.use_env = p->use_env_collisions && n_obstacles > 0;
     ap.prefetch = 4;  // 0.402 -> 0.392 ms (2, 4, 8, 16 alike; 32 is too far ahead)
     sp.do_clamp = do_clamp ? 1 : 0;
+    sp.pivot_floor = fmaxf(p->lm_lambda, 1e-30f);
 }
 
 template <class M>
@@ -829,12 +831,8 @@ static int launch_assemble(const cppflow_lm_params* p, const float* q, const flo
     SolveParams sp;
     make_params<M>(p, ob.n, 0, ap, sp);
     const size_t sh = sizeof(float) * ABLOCK * SmemLayout<M>::N_FULL;
-    static bool attr_set = false;  // per template instantiation
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(lm_assemble_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
-        if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set = true;
-    }
+    static SmemGrant granted;  // per template instantiation and device
+    if (int rc = ensure_dynamic_smem(lm_assemble_kernel<M>, sh, granted)) return rc;
     const dim3 grid(grid_for(P, ABLOCK), (unsigned)T);
     lm_assemble_kernel<M><<<grid, ABLOCK, sh, st>>>(q, xv, target, (int)P, (int)T, ob, ap, ws);
     return CPPFLOW_OK;
@@ -845,15 +843,12 @@ static int launch_solve_variant(const SolveParams& sp, const float* q, int64_t P
                                 float* ws, float* x_out, cudaStream_t st) {
     const size_t sh = SolveSmem<M::NDOF, RING>::BYTES * WARPS;
     auto kern = lm_block_solve_kernel<M, RING, WARPS>;
-    static bool attr_set = false;  // per template instantiation
-    static int prio_high = 0;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
-        if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        int least = 0, greatest = 0;
-        cudaDeviceGetStreamPriorityRange(&least, &greatest);
-        prio_high = greatest;
-        attr_set = true;
+    static SmemGrant granted;  // per template instantiation and device
+    if (int rc = ensure_dynamic_smem(kern, sh, granted)) return rc;
+    int prio_high = 0;
+    if (high_priority) {
+        int least = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &prio_high);  // of the current device
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid_for(P, 16 * WARPS));
@@ -878,12 +873,8 @@ static int launch_solve(const cppflow_lm_params* p, const float* q, int64_t P, i
     make_params<M>(p, 0, flags & CPPFLOW_LM_CLAMP, ap, sp);
     if (P <= SOLVE_RESIDENT_MAX_PATHS && solve_resident_smem<M>(T) <= 200 * 1024) {
         const size_t sh = solve_resident_smem<M>(T);
-        static size_t attr_bytes = 0;  // per template instantiation
-        if (sh > attr_bytes) {
-            cudaError_t e = cudaFuncSetAttribute(lm_block_solve_resident_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            attr_bytes = 200 * 1024;
-        }
+        static SmemGrant granted;  // per template instantiation and device
+        if (int rc = ensure_dynamic_smem(lm_block_solve_resident_kernel<M>, 200 * 1024, granted)) return rc;
         lm_block_solve_resident_kernel<M><<<(unsigned)P, 32, sh, st>>>(q, P, T, sp, ws, x_out);
         return CPPFLOW_OK;
     }

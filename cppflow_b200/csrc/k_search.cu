@@ -401,13 +401,13 @@ extern "C" int cppflow_dp_search(int robot, const float* d_q, const uint8_t* d_s
     const size_t sh_cost = 2 * (size_t)k * sizeof(float);
     const size_t sh_memo = (size_t)T * k * sizeof(uint16_t);
     cudaError_t e = cudaSuccess;
-    if (k <= 512 && T > 1) {
-        // cluster sweep: 8 CTAs split the rows, mjac prefetched in registers
-        const size_t rpc = (size_t)(k + DP_CLUSTER - 1) / DP_CLUSTER;
-        const size_t sh_base = 2 * sh_cost + rpc * T * sizeof(float);  // two (cost, argmin) pair buffers + penalties
+    // cluster sweep: 8 CTAs split the rows, mjac prefetched in registers; its per-CTA penalties [rows][T] live in shared
+    // memory, so very long paths (no limit in the reference's dp_search) take the single-CTA sweep below instead
+    const size_t rpc = (size_t)(k + DP_CLUSTER - 1) / DP_CLUSTER;
+    const size_t sh_base = 2 * sh_cost + rpc * T * sizeof(float);  // two (cost, argmin) pair buffers + penalties
+    if (k <= 512 && T > 1 && sh_base <= 200 * 1024) {
         const bool memo_smem = sh_base + sh_memo <= 200 * 1024;
         const size_t sh = sh_base + (memo_smem ? sh_memo : 0);
-        if (sh > 200 * 1024) return fail(CPPFLOW_E_INVALID, "cppflow_dp_search: T = %lld too large for the cluster sweep", (long long)T);
 #define CPPFLOW_DP_LAUNCH(RPW, VPL, PF, MS)                                                                              \
     do {                                                                                                                 \
         e = cudaFuncSetAttribute(dp_sweep_cluster_kernel<RPW, VPL, PF, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \

@@ -8,15 +8,18 @@ namespace cppflow {
 __host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
 // In-place Cholesky A = L L^T on the lower triangle of A[N][N]; the diagonal of L is stored as its RECIPROCAL
-// in dinv[] (A[i][i] keeps L[i][i]).  Pivots are floored to keep a rounding-negative pivot from producing NaNs.
+// in dinv[] (A[i][i] keeps L[i][i]).  Pivots are floored at `floor`: the callers factor matrices of the form
+// (PSD + lambda I), whose exact pivots (Schur complements) are >= lambda, so floor = lambda only ever replaces a pivot
+// that rounding pushed below its mathematical lower bound - it cannot blow a near-singular waypoint up to 1e15 the way
+// an absolute 1e-30 floor did.
 template <int N>
-__device__ __forceinline__ void chol_lower(float (&A)[N][N], float (&dinv)[N]) {
+__device__ __forceinline__ void chol_lower(float (&A)[N][N], float (&dinv)[N], float floor = 1e-30f) {
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         float s = A[j][j];
 #pragma unroll
         for (int k = 0; k < j; ++k) s = fmaf(-A[j][k], A[j][k], s);
-        s = fmaxf(s, 1e-30f);
+        s = fmaxf(s, floor);
         const float r = rsqrtf(s);
         dinv[j] = r;
         A[j][j] = s * r;
@@ -93,13 +96,13 @@ __device__ __forceinline__ float rcp_nr(float p) {
 // FMAs per pivot for N = 8, all independent of each other (the dependent chain is one reciprocal + one FMA per pivot) -
 // about 0.6x the instructions of Cholesky + triangular inverse + L^-T L^-1, with a much shorter critical path (measured
 // in the block solve: 1024 vs 1284 cycles per block, same error against the fp64 oracle).  The
-// unswept part stays the (positive definite) Schur complement, so the pivots are positive; they are floored like the
-// Cholesky pivots to keep a rounding-negative pivot from producing NaNs.
+// unswept part stays the (positive definite) Schur complement, so the pivots are positive (>= lambda for J^T J +
+// lambda I); they are floored at `floor` like the Cholesky pivots.
 template <int N>
-__device__ __forceinline__ void sweep_neg_inverse(float (&a)[N * (N + 1) / 2], float (&y)[N]) {
+__device__ __forceinline__ void sweep_neg_inverse(float (&a)[N * (N + 1) / 2], float (&y)[N], float floor = 1e-30f) {
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        const float d = rcp_nr(fmaxf(a[tri(k, k)], 1e-30f));
+        const float d = rcp_nr(fmaxf(a[tri(k, k)], floor));
         float c[N], cd[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {

@@ -68,7 +68,9 @@ struct LoopState {
     int last_valid_idx = -1, n_tls = 0, i = 0, n_sched = 0;
     double last_tl = 0.0;
     std::chrono::steady_clock::time_point t0;
-    float tag = 0.f;               // completion tag of the iteration in flight (i + 1)
+    float tag = 0.f;               // completion tag of the iteration in flight: (per-call nonce << 8) + (i mod 255) + 1
+    unsigned nonce = 0;            // distinguishes this call's tags from stale ones of an earlier (failed) call that
+                                   // shared the pinned buffer; < 2^12, so every tag is an exact float below 2^20
     bool fuse_pose = std::getenv("CPPFLOW_LM_NO_FUSE") == nullptr;  // pose step + metrics in one launch
     float* metrics_dst = nullptr;  // where the metrics kernel writes: the pinned host buffer itself when the device can
     bool zero_copy = false;        // address it (no copy engine round trip per iteration), the device scratch otherwise
@@ -101,6 +103,8 @@ struct LoopState {
                     pa.devicePointer != nullptr;
         if (!zero_copy) cudaGetLastError();  // unregistered host memory reports an error: not fatal, copy instead
         metrics_dst = zero_copy ? (float*)pa.devicePointer : d_metrics;
+        static std::atomic<unsigned> call_counter{0};
+        nonce = (call_counter.fetch_add(1, std::memory_order_relaxed) & 0xfffu) + 1u;
         t0 = std::chrono::steady_clock::now();
         done = j->max_n_steps == 0;
         return CPPFLOW_OK;
@@ -108,7 +112,7 @@ struct LoopState {
 
     int launch() {
         const cppflow_lm_loop_job* j = job;
-        tag = (float)(i + 1);
+        tag = (float)((nonce << 8) + (unsigned)(i % 255) + 1u);
         if (zero_copy) *reinterpret_cast<volatile float*>(j->h_pinned_metrics + 7) = 0.f;  // not this iteration's tag
         bool metrics_done = false;
         if (pose_pos_valid && pose_rot_valid) {
@@ -175,9 +179,10 @@ struct LoopState {
         }
         // x_is_valid (:836-923): strict '<' thresholds (evaluation_utils.py:29-75), then the collision check
         const cppflow_constraints* c = j->constraints;
-        pose_pos_valid = m[0] < c->max_allowed_position_error_cm;
-        pose_rot_valid = m[1] < c->max_allowed_rotation_error_deg;
-        const bool mjac_ok = m[2] < c->max_allowed_mjac_deg && m[3] < c->max_allowed_mjac_cm;
+        // float32 metrics against double thresholds, as the reference's `tensor < python float` comparisons do
+        pose_pos_valid = (double)m[0] < c->max_allowed_position_error_cm;
+        pose_rot_valid = (double)m[1] < c->max_allowed_rotation_error_deg;
+        const bool mjac_ok = (double)m[2] < c->max_allowed_mjac_deg && (double)m[3] < c->max_allowed_mjac_cm;
         const bool is_valid = pose_pos_valid && pose_rot_valid && mjac_ok && !(m[5] < 0.f) && !(m[6] < 0.f);
         if (is_valid) {
             last_valid_idx = i;
@@ -211,22 +216,29 @@ struct LoopState {
 extern "C" int cppflow_lm_alternating_loss_many(int n_jobs, const cppflow_lm_loop_job* jobs) {
     CPPFLOW_CHECK_ARG(n_jobs >= 0 && (n_jobs == 0 || jobs != nullptr), "jobs");
     std::vector<LoopState> st((size_t)n_jobs);
+    // on an error return no kernel of any job may still be in flight: it would write its tag into a pinned buffer
+    // (and its iterate into a workspace) that the caller is about to reuse.  The last error text is kept.
+    auto bail = [&](int rc) {
+        for (int k = 0; k < n_jobs; ++k) cudaStreamSynchronize((cudaStream_t)jobs[k].stream);
+        cudaGetLastError();
+        return rc;
+    };
     for (int k = 0; k < n_jobs; ++k)
-        if (int rc = st[k].init(&jobs[k])) return rc;
+        if (int rc = st[k].init(&jobs[k])) return bail(rc);
     for (;;) {
         int n_active = 0;
         for (int k = 0; k < n_jobs; ++k)
             if (!st[k].done) {
-                if (int rc = st[k].launch()) return rc;
+                if (int rc = st[k].launch()) return bail(rc);
                 ++n_active;
             }
         if (n_active == 0) break;
         for (int k = 0; k < n_jobs; ++k)
             if (!st[k].done)
-                if (int rc = st[k].finish()) return rc;
+                if (int rc = st[k].finish()) return bail(rc);
     }
     for (int k = 0; k < n_jobs; ++k)
-        if (int rc = st[k].finalize()) return rc;
+        if (int rc = st[k].finalize()) return bail(rc);
     return CPPFLOW_OK;
 }
 

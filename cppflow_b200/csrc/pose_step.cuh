@@ -126,7 +126,7 @@ __device__ __forceinline__ void pose_lm_update(float (&x)[M::NDOF], const float 
             for (int d = 0; d < D; ++d) s = fmaf(J[r][d], J[c][d], s);
             A[r][c] = s;
         }
-    chol_lower<6>(A, dinv);
+    chol_lower<6>(A, dinv, fmaxf(lambda, 1e-30f));  // exact pivots of J J^T + lambda I are >= lambda
     float z[6];
     chol_solve<6>(A, dinv, e, z);
     float dx[D];
@@ -147,13 +147,20 @@ __device__ __forceinline__ void pose_lm_update(float (&x)[M::NDOF], const float 
         rho[r] = s;
     }
     chol_solve<6>(A, dinv, rho, dz);
+    float step[D], chk = 0.f;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         float s = dx[d];
 #pragma unroll
         for (int r = 0; r < 6; ++r) s = fmaf(J[r][d], dz[r], s);
-        x[d] += s;
+        step[d] = s;
+        chk += s;
     }
+    // a non-finite update (it cannot come from the floored factorisation, only from non-finite inputs) must not be
+    // turned into "joint at its limit" by the clamp below: the waypoint is left where it was
+    const bool ok = fabsf(chk) <= 3.0e38f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) x[d] += ok ? step[d] : 0.f;
     if (do_clamp) clamp_limits<M>(x);
 }
 

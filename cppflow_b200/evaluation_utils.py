@@ -48,13 +48,32 @@ def joint_limits_exceeded(robot_joint_limits: List[Tuple[float, float]], qs: np.
     return any(vp > 0 for vp in pcts), pcts
 
 
+def _abs_max(v, empty=0.0) -> float:
+    if isinstance(v, torch.Tensor):
+        return float(v.abs().max()) if v.numel() > 0 else empty
+    return abs(float(v))
+
+
 def errors_are_below_threshold(max_allowed_position_error_cm, max_allowed_rotation_error_deg, max_allowed_mjac_deg,
-                               max_allowed_mjac_cm, max_pos_cm: float, max_rot_deg: float, mjac_deg: float,
-                               mjac_cm: float):
-    """evaluation_utils.py:29-75 on already-reduced maxima (strict '<', as the reference)."""
+                               max_allowed_mjac_cm, error_t_cm, error_R_deg, qdeltas_revolute_deg, qdeltas_prismatic_cm,
+                               verbosity: int = 0):
+    """evaluation_utils.py:29-75 (strict '<' on the maxima).  The four error arguments may be the reference's tensors
+    (per-waypoint errors / joint deltas, reduced here with max / abs-max) or already-reduced numbers - the CUDA
+    metrics kernel reduces them on the device (csrc/k_metrics.cu) and the host only sees the maxima."""
+    max_pos_cm = float(error_t_cm.max()) if isinstance(error_t_cm, torch.Tensor) else float(error_t_cm)
+    max_rot_deg = float(error_R_deg.max()) if isinstance(error_R_deg, torch.Tensor) else float(error_R_deg)
+    mjac_deg = _abs_max(qdeltas_revolute_deg)
+    mjac_cm = _abs_max(qdeltas_prismatic_cm)  # no prismatic joints: 0 < threshold (the reference's `else True`)
     pose_pos_valid = max_pos_cm < max_allowed_position_error_cm
     pose_rot_valid = max_rot_deg < max_allowed_rotation_error_deg
     mjac_rev_valid = mjac_deg < max_allowed_mjac_deg
     mjac_pris_valid = mjac_cm < max_allowed_mjac_cm
+    if verbosity > 0:
+        for ok, txt in ((pose_pos_valid, f"pose-position is invalid: {max_pos_cm} < {max_allowed_position_error_cm}"),
+                        (pose_rot_valid, f"pose-rotation is invalid: {max_rot_deg} < {max_allowed_rotation_error_deg}"),
+                        (mjac_rev_valid, f"mjac_rev is invalid: {mjac_deg:.3f} > {max_allowed_mjac_deg:.3f}"),
+                        (mjac_pris_valid, f"mjac_pris is invalid: {mjac_cm:.3f} > {max_allowed_mjac_cm:.3f}")):
+            if not ok:
+                print("errors_are_below_threshold() |", txt)
     return (pose_pos_valid and pose_rot_valid and mjac_rev_valid and mjac_pris_valid,
             (pose_pos_valid, pose_rot_valid, mjac_rev_valid, mjac_pris_valid))

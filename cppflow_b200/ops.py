@@ -7,6 +7,28 @@ import torch
 from . import _lib
 from ._lib import LmParamsC, ptr, stream_ptr, require_cuda, check
 
+import functools
+
+
+def _on_device(fn):
+    """Make the device of the first CUDA tensor argument current for the duration of the call.  The library opts in
+    to large shared-memory footprints and picks stream priorities per CURRENT device (cudaFuncSetAttribute is per
+    device), and `torch.cuda.current_stream(device)` is only launchable from that device's context: without this a
+    process that keeps cuda:0 current while refining tensors on cuda:1 would launch with the wrong context."""
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+
+    return wrapper
+
+
 ROBOT_IDS = {"fetch": 0, "fetch_arm": 1, "panda": 2}
 LM_CLAMP, LM_OVERLAP = 1, 2  # CPPFLOW_LM_CLAMP / CPPFLOW_LM_OVERLAP (include/cppflow_b200.h)
 
@@ -90,6 +112,7 @@ def _check_q(q: torch.Tensor, ndof: int, name="x") -> torch.Tensor:
     return q
 
 
+@_on_device
 def forward_kinematics(rid: int, ndof: int, q: torch.Tensor) -> torch.Tensor:
     q = _check_q(q, ndof)
     out = torch.empty((q.shape[0], 7), device=q.device, dtype=torch.float32)
@@ -97,6 +120,7 @@ def forward_kinematics(rid: int, ndof: int, q: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_device
 def jacobian(rid: int, ndof: int, q: torch.Tensor) -> torch.Tensor:
     q = _check_q(q, ndof)
     out = torch.empty((q.shape[0], 6, ndof), device=q.device, dtype=torch.float32)
@@ -104,6 +128,7 @@ def jacobian(rid: int, ndof: int, q: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_device
 def pose_errors(rid: int, ndof: int, q: torch.Tensor, target: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     q = _check_q(q, ndof)
     target = require_cuda(target, "target_poses")
@@ -116,6 +141,7 @@ def pose_errors(rid: int, ndof: int, q: torch.Tensor, target: torch.Tensor) -> T
     return err, cur
 
 
+@_on_device
 def lm_pose_step(rid: int, ndof: int, params: LmParamsC, q: torch.Tensor, target: torch.Tensor, clamp: bool,
                  return_residual: bool = False, out: Optional[torch.Tensor] = None):
     q = _check_q(q, ndof)
@@ -133,6 +159,7 @@ def lm_pose_step(rid: int, ndof: int, params: LmParamsC, q: torch.Tensor, target
     return x_out
 
 
+@_on_device
 def lm_pose_steps_(rid: int, ndof: int, params: LmParamsC, lambdas, q: torch.Tensor, target: torch.Tensor,
                    clamp: bool = True) -> torch.Tensor:
     """len(lambdas) pose-only LM steps in place on q (step i with damping lambdas[i]): one library call."""
@@ -146,6 +173,7 @@ def lm_pose_steps_(rid: int, ndof: int, params: LmParamsC, lambdas, q: torch.Ten
     return q
 
 
+@_on_device
 def clamp_to_joint_limits_(rid: int, ndof: int, q: torch.Tensor) -> torch.Tensor:
     assert q.is_cuda and q.dtype == torch.float32 and q.is_contiguous(), "in-place clamp needs a contiguous fp32 CUDA tensor"
     assert q.dim() == 2 and q.shape[1] == ndof
@@ -153,6 +181,7 @@ def clamp_to_joint_limits_(rid: int, ndof: int, q: torch.Tensor) -> torch.Tensor
     return q
 
 
+@_on_device
 def self_collision_distances(rid: int, ndof: int, n_pairs: int, q: torch.Tensor, with_jacobian: bool = False):
     q = _check_q(q, ndof)
     n = q.shape[0]
@@ -162,6 +191,7 @@ def self_collision_distances(rid: int, ndof: int, n_pairs: int, q: torch.Tensor,
     return (d, J) if with_jacobian else d
 
 
+@_on_device
 def env_collision_distances(rid: int, ndof: int, n_caps: int, q: torch.Tensor, ob: Obstacles, index: int = 0,
                             with_jacobian: bool = False):
     q = _check_q(q, ndof)
@@ -174,6 +204,7 @@ def env_collision_distances(rid: int, ndof: int, n_caps: int, q: torch.Tensor, o
     return (d, J) if with_jacobian else d
 
 
+@_on_device
 def collision_flags(rid: int, ndof: int, q: torch.Tensor, ob: Optional[Obstacles], want_self=True, want_env=True):
     q = _check_q(q, ndof)
     n = q.shape[0]
@@ -198,6 +229,7 @@ def _workspace(device, nbytes: int, key: str) -> torch.Tensor:
     return buf
 
 
+@_on_device
 def lm_full_step(rid: int, ndof: int, params: LmParamsC, q: torch.Tensor, xv: Optional[torch.Tensor],
                  target: Optional[torch.Tensor], P: int, T: int, ob: Optional[Obstacles], clamp: bool,
                  out: Optional[torch.Tensor] = None, overlap: bool = False,
@@ -228,6 +260,7 @@ def lm_full_step(rid: int, ndof: int, params: LmParamsC, q: torch.Tensor, xv: Op
     return x_out
 
 
+@_on_device
 def joint_limit_flags(rid: int, ndof: int, q2d: torch.Tensor, eps_revolute: float, eps_prismatic: float) -> torch.Tensor:
     q2d = _check_q(q2d, ndof, "qs")
     out = torch.empty((q2d.shape[0],), device=q2d.device, dtype=torch.float32)
@@ -236,6 +269,7 @@ def joint_limit_flags(rid: int, ndof: int, q2d: torch.Tensor, eps_revolute: floa
     return out
 
 
+@_on_device
 def dp_search(rid: int, ndof: int, q: torch.Tensor, self_flags: torch.Tensor, env_flags: torch.Tensor):
     """-> best_path [T,D], memo int32 [k,T], costs [k,T], chosen int32 [T]"""
     q = require_cuda(q, "q")
@@ -258,6 +292,7 @@ def dp_search(rid: int, ndof: int, q: torch.Tensor, self_flags: torch.Tensor, en
 METRIC_NAMES = ("max_pos_cm", "max_rot_deg", "mjac_deg", "mjac_cm", "tl", "min_self", "min_env")
 
 
+@_on_device
 def path_metrics(rid: int, ndof: int, q: torch.Tensor, target: torch.Tensor, P: int, T: int,
                  ob: Optional[Obstacles]) -> torch.Tensor:
     q = _check_q(q, ndof)
@@ -273,6 +308,7 @@ def path_metrics(rid: int, ndof: int, q: torch.Tensor, target: torch.Tensor, P: 
 _PINNED = {}
 
 
+@_on_device
 def lm_alternating_loss(rid: int, ndof: int, params_diff: LmParamsC, params_pose: LmParamsC, constraints,
                         x_seed: torch.Tensor, target: torch.Tensor, T: int, ob: Optional[Obstacles], max_n_steps: int,
                         tmax_sec: float, return_if_valid_after_n_steps: int, convergence_threshold: float):

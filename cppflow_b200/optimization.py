@@ -125,7 +125,13 @@ def run_lm_alternating_loss(opt_problem: OptimizationProblem, opt_state: Optimiz
     `run_lm_alternating_loss_python` is the same loop in Python, kept for the mesh-validator callback, for
     verbosity > 1 and as the cross-check of the native loop (tests/test_gpu_planner.py)."""
     assert opt_problem.parallel_count == 1, "the alternating loop is per path; batch with run_lm_fixed_schedule"
-    assert not save_images and not return_residuals, "debug outputs of the reference are not reproduced"
+    if save_images or return_residuals:
+        raise NotImplementedError("save_images / return_residuals (debug outputs of the reference's loop) are not reproduced")
+    if results_df is not None:
+        # the reference logs every iterate through Problem.write_qpath_to_results_df, which itself raises
+        # NotImplementedError (data_types.py:419-420): passing a results_df fails there too, it is never silently ignored
+        raise NotImplementedError("results_df logging is not available (Problem.write_qpath_to_results_df raises in the "
+                                  "reference as well, data_types.py:419-420)")
     if tmax_sec is None:
         assert (max_n_steps is not None) and (return_if_valid_after_n_steps is not None)
         assert return_if_valid_after_n_steps <= max_n_steps

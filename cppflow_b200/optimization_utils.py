@@ -54,6 +54,8 @@ def x_is_valid(problem: Problem, constraints: Constraints, target_path_stacked: 
                metrics: Optional[torch.Tensor] = None):
     """Returns (x_i or None, i or None, (pose_pos_valid, pose_rot_valid, mjac_rev_valid, mjac_pris_valid,
     is_a_self_collision, is_a_env_collision)) like the reference; the flags are those of the last path examined."""
+    if results_df is not None:
+        raise NotImplementedError("results_df logging is not available (data_types.py:419-420 raises in the reference too)")
     n = problem.n_timesteps
     assert x.shape[0] == n * parallel_count
     m = (path_metrics(problem, x, parallel_count) if metrics is None else metrics).cpu()  # the ONE sync per call

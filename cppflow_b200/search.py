@@ -22,11 +22,12 @@ def joint_limit_almost_violations_3d(robot, qs: torch.Tensor, eps_revolute: floa
 
 
 def dp_search(robot, q: torch.Tensor, self_collision_violations: torch.Tensor, env_collision_violations: torch.Tensor,
-              use_cuda: bool = True, verbosity: int = 1, return_details: bool = False):
+              use_cuda: bool = False, verbosity: int = 1, return_details: bool = False):
     """q [k, T, ndof] -> best path [T, ndof] (search.py:128-173).
 
-    `use_cuda` is accepted for signature compatibility; the search always runs on the device q lives on
-    (the reference defaults to moving q to the CPU, search.py:140-141 - there is no CPU path here)."""
+    `use_cuda` is accepted (with the reference's default) for signature compatibility and ignored: the search always
+    runs on the device q lives on and the path is returned there.  The reference moves q to the CPU unless use_cuda is
+    set (search.py:140-141) and its caller moves the result back (`.to(DEVICE)`, planners.py:274) - a no-op here."""
     best, memo, costs, chosen = ops.dp_search(robot.robot_id, robot.ndof, q, self_collision_violations,
                                               env_collision_violations)
     if return_details:

@@ -39,10 +39,16 @@ def cuboid_tensors(obstacles):
     return cuboids, Tcuboids
 
 
+# A second workload of the same shape whose reference joint path stays clear of the four cuboids (the default path,
+# seed 0 / amplitude 0.25, drives the upper arm THROUGH a cuboid: no path of that batch can ever be valid, which is
+# fine for timing the kernels but leaves the cost argmin nothing to choose from).
+FEASIBLE = dict(seed=3, amp=0.08)
+
+
 def synthetic_seeds_host(robot: Robot, P: int, T: int, seed: int = 0, noise: float = 0.05, shard: int = 0,
-                         pin: bool = False):
+                         pin: bool = False, amp: float = 0.25):
     """-> (q* [T, D] float32 host, x0 [P*T, D] float32 host (optionally pinned))."""
-    qstar = torch.tensor(smooth_joint_path(robot.actuated_joints_limits, T, seed), dtype=torch.float32)
+    qstar = torch.tensor(smooth_joint_path(robot.actuated_joints_limits, T, seed, amp), dtype=torch.float32)
     g = torch.Generator().manual_seed(1234 + shard)
     x0 = qstar[None] + noise * torch.randn((P, T, robot.ndof), generator=g)
     lim = torch.tensor(robot.actuated_joints_limits, dtype=torch.float32)
@@ -52,8 +58,9 @@ def synthetic_seeds_host(robot: Robot, P: int, T: int, seed: int = 0, noise: flo
     return qstar, x0
 
 
-def synthetic_problem(robot: Robot, T: int, seed: int = 0, obstacles=FETCH_CIRCLE_OBSTACLES, device="cuda:0") -> Problem:
-    qstar = torch.tensor(smooth_joint_path(robot.actuated_joints_limits, T, seed), dtype=torch.float32)
+def synthetic_problem(robot: Robot, T: int, seed: int = 0, obstacles=FETCH_CIRCLE_OBSTACLES, device="cuda:0",
+                      amp: float = 0.25) -> Problem:
+    qstar = torch.tensor(smooth_joint_path(robot.actuated_joints_limits, T, seed, amp), dtype=torch.float32)
     target = robot.forward_kinematics(qstar.to(device))
     cuboids, Tcuboids = cuboid_tensors(obstacles)
     return Problem(DEFAULT_CONSTRAINTS, target, None, robot, "synthetic", f"{robot.name}__synthetic", list(obstacles),

@@ -79,6 +79,13 @@ typedef struct cppflow_robot_info {
 const char* cppflow_version(void);
 const char* cppflow_last_error(void);
 
+/* ABI check for foreign-function bindings: out[0] = CPPFLOW_ABI_VERSION, then sizeof of cppflow_lm_params,
+ * cppflow_robot_info, cppflow_constraints, cppflow_lm_loop_result, cppflow_lm_loop_job (as many as fit in n).
+ * Returns the number of values the library knows (6).  A binding compares them with its own struct sizes after
+ * dlopen and refuses a library built from another header. */
+#define CPPFLOW_ABI_VERSION 2
+int cppflow_abi_info(int64_t* out, int n);
+
 /* jrl.Robot properties (ndof, actuated_joints_limits, prismatic_joint_idxs, _collision_capsules_by_link). */
 int cppflow_robot_info_get(int robot, cppflow_robot_info* out);
 
@@ -161,13 +168,16 @@ int cppflow_lm_full_solve(int robot, const cppflow_lm_params* params, const floa
  * thresholds of evaluation_utils.py:29-75 (strict <) and non-negative capsule distances (the reference's klampt mesh
  * checks, optimization_utils.py:889-900, are out of scope; the Python host keeps a loop with a mesh callback).
  * UNLIKE the other entry points this one BLOCKS: like the reference (`.item()`, :175) it reads the metrics of every
- * iterate on the host - 8 floats into `h_pinned_metrics` (page-locked host memory) and one cudaStreamSynchronize per
- * iteration.  Workspace: cppflow_lm_alternating_workspace_bytes(robot, T) bytes, 256-byte aligned. */
+ * iterate on the host - the metrics kernel stores its 8 floats straight into `h_pinned_metrics` (page-locked,
+ * device-mapped host memory) followed by a per-call completion tag, which the host polls (no cudaStreamSynchronize per
+ * iteration; a stream synchronisation is the fallback when the buffer is not device-addressable or the tag does not
+ * show up).  Workspace: cppflow_lm_alternating_workspace_bytes(robot, T) bytes, 256-byte aligned.
+ * The thresholds are doubles, like the Python floats the reference compares its float32 metrics with. */
 typedef struct cppflow_constraints { /* data_types.py:53-62 */
-    float max_allowed_position_error_cm;
-    float max_allowed_rotation_error_deg;
-    float max_allowed_mjac_deg;
-    float max_allowed_mjac_cm;
+    double max_allowed_position_error_cm;
+    double max_allowed_rotation_error_deg;
+    double max_allowed_mjac_deg;
+    double max_allowed_mjac_cm;
 } cppflow_constraints;
 #define CPPFLOW_LM_SCHEDULE_MAX 256
 typedef struct cppflow_lm_loop_result { /* OptimizationResult, optimization.py:52-57 */

@@ -259,3 +259,82 @@ def test_standalone_clamp_vs_golden(robots, golden, r):
     assert y.data_ptr() == x.data_ptr()
     assert np.array_equal(x.cpu().numpy(), golden[f"{r}/lm/clamp_out"])
     assert not np.array_equal(golden[f"{r}/lm/clamp_in"], golden[f"{r}/lm/clamp_out"])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# robustness items of the round-1 review
+
+
+@pytest.mark.parametrize("r", ROBOTS)
+def test_pose_step_at_kinematic_singularities(robots, r):
+    """Fully stretched / aligned-axes configurations: J J^T + lambda I is numerically singular (pivots at the lambda
+    floor).  The update must stay finite and follow the exact LM step to the tolerance used for ill-conditioned
+    waypoints (2 % of the step) - never be thrown to a joint limit by a blown-up pivot."""
+    from cppflow_b200 import ops
+    from cppflow_b200.lm_hyper_parameters import ALT_LOSS_V2_1_POSE
+
+    m = R.get_model(r)
+    rob = robots[r]
+    D = m.ndof
+    lim = torch.tensor(m.actuated_joints_limits, dtype=torch.float64)
+    base = torch.zeros(D, dtype=torch.float64).clamp(lim[:, 0], lim[:, 1])  # stretched arm (inside the limits)
+    g = torch.Generator().manual_seed(5)
+    xs = [base]
+    for eps in (1e-6, 1e-4, 1e-2):
+        xs += [(base + eps * torch.randn(D, generator=g, dtype=torch.float64)).clamp(lim[:, 0], lim[:, 1]) for _ in range(5)]
+    x = torch.stack(xs).float()
+    from oracle import kinematics as K
+
+    target = K.forward_kinematics(m, (x.double() + 0.01 * torch.randn(x.shape, generator=g, dtype=torch.float64)).clamp(lim[:, 0], lim[:, 1])).float()
+    out = ops.lm_pose_step(rob.robot_id, D, ops.make_params(ALT_LOSS_V2_1_POSE), x.to(DEV), target.to(DEV), True).cpu()
+    assert torch.isfinite(out).all()
+    ref = L.clamp_to_joint_limits(m, L.levenberg_marquardt_only_pose(m, x.double(), target.double(), L.ALT_LOSS_V2_1_POSE))
+    step = (ref - x.double()).abs().max(dim=1).values
+    err = (out.double() - ref).abs().max(dim=1).values
+    assert (err <= 2e-2 * torch.clamp(step, min=1.0)).all(), (err, step)
+
+
+def test_second_device(robots):
+    """Tensors on cuda:1 while cuda:0 stays the current device: the shared-memory opt-in of the big kernels is per
+    device and the ops make the tensor's device current for the call.  Same results as on cuda:0, bit for bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from cppflow_b200 import ops
+    from cppflow_b200.lm_hyper_parameters import all_terms_parameters
+
+    rob = robots["fetch"]
+    P, T = 300, 64
+    m, target, x0 = synthetic_problem("fetch", P, T, seed=3)
+    cuboids, Tcuboids = cuboid_tensors(OBSTACLES["fetch"])
+    ob = ops.Obstacles(cuboids, Tcuboids)
+    prm = ops.make_params(all_terms_parameters())
+    outs = []
+    assert torch.cuda.current_device() == 0
+    for dev in ("cuda:0", "cuda:1"):
+        x, tg = x0.to(dev), target.to(dev)
+        y = ops.lm_full_step(rob.robot_id, rob.ndof, prm, x, None, tg, P, T, ob, True)
+        y1 = ops.lm_full_step(rob.robot_id, rob.ndof, prm, x[:T].contiguous(), None, tg, 1, T, ob, True)  # resident solve
+        mt = ops.path_metrics(rob.robot_id, rob.ndof, y, tg, P, T, ob)
+        outs.append((y.cpu(), y1.cpu(), mt.cpu()))
+        assert torch.cuda.current_device() == 0
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+def test_dp_search_long_path_takes_the_single_cta_sweep(robots):
+    """k <= 512 candidates but a path too long for the cluster sweep's shared-memory penalties: the search must fall
+    through to the single-CTA sweep (the reference's dp_search has no limit on T), bit-exact as ever."""
+    from cppflow_b200 import ops
+    from oracle import search as S
+
+    m = R.get_model("panda")
+    rob = robots["panda"]
+    k, T = 24, 20000  # 3 rows per CTA x 20000 x 4 B = 240 KB of penalties > 200 KB
+    g = torch.Generator().manual_seed(3)
+    base = random_configs(m, 1, seed=4)[0]
+    q = base[None, None] + 0.05 * torch.randn((k, T, m.ndof), generator=g).cumsum(dim=1) * 0.05
+    sv = torch.rand((k, T), generator=g) < 0.1
+    ev = torch.rand((k, T), generator=g) < 0.1
+    best, memo, costs, chosen = ops.dp_search(rob.robot_id, rob.ndof, q.to(DEV), sv.to(DEV), ev.to(DEV))
+    ref_best, ref_memo, ref_costs, ref_chosen = S.dp_search(m, q, sv, ev)
+    assert torch.equal(memo.cpu(), ref_memo) and torch.equal(costs.cpu(), ref_costs) and torch.equal(best.cpu(), ref_best)

@@ -109,7 +109,7 @@ def test_problem_loader_matches_reference_files():
 
 
 def test_shard_range_and_costs():
-    from cppflow_b200.distributed import shard_range, path_costs, INVALID_COST
+    from cppflow_b200.distributed import shard_range, path_costs, path_keys, decode_key, INVALID_COST
 
     for n, w in [(8192, 8), (13, 4), (3, 8)]:
         spans = [shard_range(n, r, w) for r in range(w)]
@@ -119,47 +119,73 @@ def test_shard_range_and_costs():
     m = torch.tensor([[0.001, 0.01, 1.0, 0.1, 3.0, 0.1, 0.1, 0], [0.5, 0.01, 1.0, 0.1, 2.0, 0.1, 0.1, 0],
                       [0.001, 0.01, 1.0, 0.1, 2.5, 0.1, -0.1, 0]])
     c = path_costs(m, DEFAULT_CONSTRAINTS)
-    assert c.tolist() == pytest.approx([3.0, 2.0 + INVALID_COST, 2.5 + INVALID_COST])
+    assert c.dtype == torch.float64
+    assert c.tolist() == pytest.approx([3.0, 2.0 + INVALID_COST, 2.5 + INVALID_COST], abs=1e-6)
+    # the packed keys order like (invalid, TL, index) and survive the round trip
+    keys = path_keys(m, DEFAULT_CONSTRAINTS, first_index=100).tolist()
+    assert [decode_key(k) for k in keys] == [(True, 3.0, 100), (False, 2.0, 101), (False, 2.5, 102)]
+    assert sorted(range(3), key=lambda i: keys[i]) == [0, 1, 2]
+    # among invalid paths the trajectory length still decides (float32 TL + 1e9 could not tell 2.0 from 2.5)
+    assert keys[1] < keys[2] and float(torch.tensor(2.0) + 1e9) == float(torch.tensor(2.5) + 1e9)
+    nan = m.clone()
+    nan[0, 4] = float("nan")
+    assert decode_key(int(path_keys(nan, DEFAULT_CONSTRAINTS)[0]))[0] is False
 
 
-def _gather_worker(rank, world, port, out):
+def _gather_worker(rank, world, port, out, all_invalid):
     import torch.distributed as dist
-    from cppflow_b200.distributed import gather_costs_and_argmin, shard_range
+    from cppflow_b200.distributed import enqueue_argmin, gather_costs_and_argmin, shard_range
 
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    metrics = _gather_metrics(all_invalid)
+    s, e = shard_range(metrics.shape[0], rank, world)
+    best = gather_costs_and_argmin(metrics[s:e], DEFAULT_CONSTRAINTS, rank, world, first_index=s)
+    full = enqueue_argmin(metrics[s:e], DEFAULT_CONSTRAINTS, s, world).result()
+    out[rank] = (best, (s, e), tuple(full))
+    dist.destroy_process_group()
+
+
+def _gather_metrics(all_invalid):
     g = torch.Generator().manual_seed(0)
     P = 37
     metrics = torch.zeros((P, 8))
     metrics[:, 4] = torch.rand(P, generator=g) + 1.0  # trajectory lengths
     metrics[:, 5:7] = 0.1
     metrics[5, 4] = metrics[29, 4] = 0.5              # tie across shards -> lowest global index wins
-    s, e = shard_range(P, rank, world)
-    best = gather_costs_and_argmin(metrics[s:e], DEFAULT_CONSTRAINTS, rank, world)
-    out[rank] = (best, (s, e))
-    dist.destroy_process_group()
+    if all_invalid:
+        metrics[:, 0] = 1.0                           # every path breaks the position threshold
+        metrics[20, 4] = 0.25                         # ... and the shortest of them lives in the second shard
+    else:
+        metrics[20, 4] = 0.25                         # shorter than the tie but invalid
+        metrics[20, 6] = -0.01
+    return metrics
 
 
-def test_gather_argmin_two_ranks_gloo():
-    """the argmin is invariant to the shard count."""
+@pytest.mark.parametrize("all_invalid", [False, True])
+def test_gather_argmin_two_ranks_gloo(all_invalid):
+    """the argmin is invariant to the shard count - also when every path is invalid, where the ranking
+    falls back to the trajectory length among invalid paths (round 1's float32 `TL + 1e9` lost it to rounding)."""
+    from cppflow_b200.distributed import gather_costs_and_argmin, INVALID_COST
+
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_gather_worker, args=(2, port, out), nprocs=2, join=True)
-    (b0, span0), (b1, span1) = out[0], out[1]
-    assert b0 == b1
+    mp.spawn(_gather_worker, args=(2, port, out, all_invalid), nprocs=2, join=True)
+    (b0, span0, f0), (b1, span1, f1) = out[0], out[1]
+    assert b0 == b1 and f0 == f1
     cost, rank, idx = b0
-    assert cost == pytest.approx(0.5) and rank == 0 and span0[0] + idx == 5
-    from cppflow_b200.distributed import gather_costs_and_argmin
-
-    g = torch.Generator().manual_seed(0)
-    metrics = torch.zeros((37, 8))
-    metrics[:, 4] = torch.rand(37, generator=g) + 1.0
-    metrics[:, 5:7] = 0.1
-    metrics[5, 4] = metrics[29, 4] = 0.5
-    assert gather_costs_and_argmin(metrics, DEFAULT_CONSTRAINTS, 0, 1) == (pytest.approx(0.5), 0, 5)
+    single = gather_costs_and_argmin(_gather_metrics(all_invalid), DEFAULT_CONSTRAINTS, 0, 1)
+    if all_invalid:
+        assert cost == pytest.approx(0.25 + INVALID_COST) and rank == 1 and span1[0] + idx == 20
+        assert f0[3] == 0 and f0[4] is False  # n_valid, valid
+        assert single == (pytest.approx(0.25 + INVALID_COST), 0, 20)
+    else:
+        assert cost == pytest.approx(0.5) and rank == 0 and span0[0] + idx == 5
+        assert f0[3] == 36 and f0[4] is True and f0[6] == 5
+        assert single == (pytest.approx(0.5), 0, 5)
 
 
 def test_split_paths_covers_every_path_once():
