@@ -17,6 +17,8 @@
 // thread and writes the packed (A_tt, b_t) block (44 floats for D = 8) to the workspace.
 // Kernel B (solve) runs a twisted block-Thomas elimination per path (two lanes per path, one from each end), streaming
 // the blocks in with TMA bulk copies, and writes clamp(x + dx).  Nothing of size (T*D)^2 is ever formed.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "collision.cuh"
 #include "linalg.cuh"
@@ -789,6 +791,186 @@ lm_block_solve_resident_kernel(const float* __restrict__ q, int64_t P, int64_t T
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// The same twisted sweep with the blocks held in REGISTERS only: every lane loads its own path's block with eleven
+// coalesced 16-byte loads (lanes = consecutive paths, so a warp instruction covers 2 x 256 contiguous bytes, one run
+// per sweep direction), one step AHEAD of its use, and stores the result straight back.  No shared memory, no
+// mbarriers, no TMA: a lane only ever re-reads what it wrote itself (same-thread ordering through global memory), so
+// no fence and no read token is needed either.  Per step a warp issues ~11 LDG + S-update + sweep + 11 STG; the
+// TMA-ring kernel above spends about as many cycles again on ring bookkeeping (mbarrier wait, LDS, token REDUX,
+// re-arming).  Bit-identical to it: same lane <-> (path, side) mapping, same arithmetic in the same order.
+// WARPS per CTA: 4 (one per scheduler) or 8 (two per scheduler: the second hides the first one's load and
+// fixed-latency stalls).
+template <class M, int WARPS, bool PREFETCH>
+__global__ void __launch_bounds__(32 * WARPS, 1)
+lm_block_solve_v2_kernel(const float* __restrict__ q, int64_t P, int64_t T, const SolveParams prm, float* __restrict__ ws,
+                         float* __restrict__ x_out) {
+    constexpr int D = M::NDOF;
+    constexpr int NT = BlockLayout<D>::NT;
+    constexpr int NW = BlockLayout<D>::NW;
+    constexpr int NV = NW / 4;
+    constexpr int64_t BLK_F4 = NV * 16;  // float4 per 16-path block
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t g = (int64_t)blockIdx.x * WARPS + warp;  // 16-path group of this warp
+    if (g * 16 >= P) return;
+    const int side = lane & 1, l = lane >> 1;
+    const int64_t p_raw = g * 16 + l;
+    const bool active = p_raw < P;
+    const int64_t p = active ? p_raw : P - 1;  // idle lanes (P % 16 != 0) work on the group's padding and never store x
+    float4* wsg = reinterpret_cast<float4*>(ws) + g * T * BLK_F4 + l;  // float4 k of block t: wsg[t * BLK_F4 + k * 16]
+    const float* qp = q + p * T * D;
+    const int64_t m = T / 2;
+    const int64_t n0 = m, n1 = T - 1 - m;  // blocks eliminated by side 0 / side 1
+    const int64_t n_side = side == 0 ? n0 : n1;
+    const BetaSel<M> bs(prm.b_rev, prm.b_pri);
+    auto t_of = [&](int64_t k) { return side == 0 ? k : T - 1 - k; };
+    auto load_blk = [&](int64_t t, float (&v)[NW]) {
+        const float4* src = wsg + t * BLK_F4;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const float4 f = src[k * 16];
+            v[4 * k] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w;
+        }
+    };
+    auto store_x = [&](int64_t t, float (&xn)[D]) {
+        if (prm.do_clamp) {
+            static_for<D>([&](auto Dd) {
+                constexpr int d = decltype(Dd)::value;
+                xn[d] = fminf(fmaxf(xn[d], dof_lower<M>(d)), dof_upper<M>(d));
+            });
+        }
+        float* xo = x_out + (p * T + t) * D;
+        if constexpr (D % 4 == 0) {
+#pragma unroll
+            for (int d = 0; d < D; d += 4)
+                *reinterpret_cast<float4*>(xo + d) = make_float4(xn[d], xn[d + 1], xn[d + 2], xn[d + 3]);
+        } else {
+#pragma unroll
+            for (int d = 0; d < D; ++d) xo[d] = xn[d];
+        }
+    };
+
+    float nS[NT], u[D];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) nS[k] = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) u[d] = 0.f;
+
+    // ---- elimination: S_t = A_t + (beta beta^T) . nS,  y_t = b_t + beta . u_in;  block t <- (-S_t^-1, u_t)
+    float nxt[NW];
+    if (PREFETCH && n_side > 0) load_blk(t_of(0), nxt);
+    for (int64_t k = 0; k < n_side; ++k) {
+        float blk[NW];
+        if constexpr (PREFETCH) {
+#pragma unroll
+            for (int i = 0; i < NW; ++i) blk[i] = nxt[i];
+            if (k + 1 < n_side) load_blk(t_of(k + 1), nxt);
+        } else {
+            load_blk(t_of(k), blk);
+        }
+        static_for<D>([&](auto Ii) {
+            constexpr int i = decltype(Ii)::value;
+            u[i] = fmaf(bs.template b<i>(), u[i], blk[NT + i]);
+            static_for<i + 1>([&](auto Jj) {
+                constexpr int j = decltype(Jj)::value;
+                nS[tri(i, j)] = fmaf(bs.template bb<i, j>(), nS[tri(i, j)], blk[tri(i, j)]);
+            });
+        });
+        sweep_neg_inverse<D>(nS, u, prm.pivot_floor);
+        float v[NW];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) v[i] = nS[i];
+#pragma unroll
+        for (int d = 0; d < D; ++d) v[NT + d] = u[d];
+#pragma unroll
+        for (int i = NT + D; i < NW; ++i) v[i] = 0.f;
+        float4* dst = wsg + t_of(k) * BLK_F4;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) dst[i * 16] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+
+    // first back-substitution block and q row on their way while the middle block is factorised
+    float qn[D];
+    auto load_qrow = [&](int64_t t, float (&v)[D]) {
+        if constexpr (D % 4 == 0) {
+#pragma unroll
+            for (int d = 0; d < D; d += 4) {
+                const float4 f = __ldg(reinterpret_cast<const float4*>(qp + t * D + d));
+                v[d] = f.x; v[d + 1] = f.y; v[d + 2] = f.z; v[d + 3] = f.w;
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < D; ++d) v[d] = __ldg(qp + t * D + d);
+        }
+    };
+    if (PREFETCH && n_side > 0) {
+        load_blk(t_of(n_side - 1), nxt);
+        load_qrow(t_of(n_side - 1), qn);
+    }
+
+    // ---- middle block: S_m = A_m + (beta beta^T) . (nS_left + nS_right),  y_m = b_m + beta . (u_left + u_right)
+    __syncwarp();
+    float dx[D];
+    {
+        float Sm[NT];
+        float blk[NW];
+        load_blk(m, blk);  // both lanes of the pair read the middle block (same address)
+        static_for<D>([&](auto Ii) {
+            constexpr int i = decltype(Ii)::value;
+            const float uo = __shfl_xor_sync(0xffffffffu, u[i], 1);
+            dx[i] = fmaf(bs.template b<i>(), u[i] + uo, blk[NT + i]);
+            static_for<i + 1>([&](auto Jj) {
+                constexpr int j = decltype(Jj)::value;
+                const float so = __shfl_xor_sync(0xffffffffu, nS[tri(i, j)], 1);
+                Sm[tri(i, j)] = fmaf(bs.template bb<i, j>(), nS[tri(i, j)] + so, blk[tri(i, j)]);
+            });
+        });
+        sweep_neg_inverse<D>(Sm, dx, prm.pivot_floor);  // both lanes of the pair compute dx_m
+        if (side == 0 && active) {
+            float xn[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) xn[i] = __ldg(qp + m * D + i) + dx[i];
+            store_x(m, xn);
+        }
+    }
+
+    // ---- back-substitution outwards from the middle: dx_t = u_t - nS_t (beta . dx_inner)
+    for (int64_t k = n_side - 1; k >= 0; --k) {
+        float blk[NW], xn[D];
+        if constexpr (PREFETCH) {
+#pragma unroll
+            for (int i = 0; i < NW; ++i) blk[i] = nxt[i];
+#pragma unroll
+            for (int d = 0; d < D; ++d) xn[d] = qn[d];
+            if (k > 0) {
+                load_blk(t_of(k - 1), nxt);
+                load_qrow(t_of(k - 1), qn);
+            }
+        } else {
+            load_blk(t_of(k), blk);
+            load_qrow(t_of(k), xn);
+        }
+        float z[D];
+        static_for<D>([&](auto Ii) {
+            constexpr int i = decltype(Ii)::value;
+            z[i] = bs.template b<i>() * dx[i];
+        });
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            float a0 = blk[NT + i], a1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < D; j += 2) {
+                a0 = fmaf(-(j <= i ? blk[tri(i, j)] : blk[tri(j, i)]), z[j], a0);
+                if (j + 1 < D) a1 = fmaf(-(j + 1 <= i ? blk[tri(i, j + 1)] : blk[tri(j + 1, i)]), z[j + 1], a1);
+            }
+            dx[i] = a0 + a1;
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) xn[i] += dx[i];
+        if (active) store_x(t_of(k), xn);
+    }
+}
+
 constexpr int64_t SOLVE_RESIDENT_MAX_PATHS = 8;  // beyond a handful of paths the streaming kernel's throughput wins
 
 template <class M>
@@ -865,6 +1047,26 @@ static int launch_solve_variant(const SolveParams& sp, const float* q, int64_t P
     return CPPFLOW_OK;
 }
 
+template <class M, int WARPS, bool PREFETCH>
+static int launch_solve_v2(const SolveParams& sp, const float* q, int64_t P, int64_t T, bool high_priority, float* ws,
+                           float* x_out, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid_for(P, 16 * WARPS));
+    cfg.blockDim = dim3(32 * WARPS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributePriority;
+    int least = 0, greatest = 0;
+    if (high_priority) cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    at[0].val.priority = greatest;
+    cfg.attrs = at;
+    cfg.numAttrs = high_priority ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lm_block_solve_v2_kernel<M, WARPS, PREFETCH>, q, P, T, sp, ws, x_out);
+    if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "lm_block_solve_v2 launch: %s", cudaGetErrorString(e));
+    return CPPFLOW_OK;
+}
+
 template <class M>
 static int launch_solve(const cppflow_lm_params* p, const float* q, int64_t P, int64_t T, int flags, float* ws,
                         float* x_out, cudaStream_t st) {
@@ -878,6 +1080,25 @@ static int launch_solve(const cppflow_lm_params* p, const float* q, int64_t P, i
         lm_block_solve_resident_kernel<M><<<(unsigned)P, 32, sh, st>>>(q, P, T, sp, ws, x_out);
         return CPPFLOW_OK;
     }
+    // experiment switch (profiles/r02_notes.md): CPPFLOW_SOLVE = "tma" (ring kernel), "tma8r3" (8 warps, 3-slot ring: a
+    // whole-SM CTA), "v2w1" / "v2w2" / "v2w4" / "v2w8" (register-resident kernel, warps per CTA), suffix "np" = no prefetch
+    static const char* which = std::getenv("CPPFLOW_SOLVE");
+    if (which && std::strncmp(which, "v2", 2) == 0) {
+        const bool np = std::strstr(which, "np") != nullptr;
+        const bool hp = (flags & CPPFLOW_LM_OVERLAP) != 0;
+        const int w = std::strstr(which, "w8") ? 8 : std::strstr(which, "w2") ? 2 : std::strstr(which, "w1") ? 1 : 4;
+        if (np) return w == 8 ? launch_solve_v2<M, 8, false>(sp, q, P, T, hp, ws, x_out, st) : launch_solve_v2<M, 4, false>(sp, q, P, T, hp, ws, x_out, st);
+        switch (w) {
+            case 1: return launch_solve_v2<M, 1, true>(sp, q, P, T, hp, ws, x_out, st);
+            case 2: return launch_solve_v2<M, 2, true>(sp, q, P, T, hp, ws, x_out, st);
+            case 8: return launch_solve_v2<M, 8, true>(sp, q, P, T, hp, ws, x_out, st);
+            default: return launch_solve_v2<M, 4, true>(sp, q, P, T, hp, ws, x_out, st);
+        }
+    }
+    if (which && std::strcmp(which, "tma8r3") == 0)
+        return launch_solve_variant<M, 3, 8>(sp, q, P, T, (flags & CPPFLOW_LM_OVERLAP) != 0, ws, x_out, st);
+    if (which && std::strcmp(which, "tma1") == 0)
+        return launch_solve_variant<M, 4, 1>(sp, q, P, T, (flags & CPPFLOW_LM_OVERLAP) != 0, ws, x_out, st);
     if (flags & CPPFLOW_LM_OVERLAP) return launch_solve_variant<M, SOLVE_RING_OVERLAP>(sp, q, P, T, true, ws, x_out, st);
     return launch_solve_variant<M, SOLVE_RING_ALONE>(sp, q, P, T, false, ws, x_out, st);
 }

@@ -187,6 +187,218 @@ path_metrics_kernel(const float* __restrict__ q_in, const float* __restrict__ ta
     }
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------
+// Many paths (the batch refinement's cost / validity tail: thousands of paths at once): one CTA per path, BLOCK chosen
+// at launch so that the path's waypoints fill the CTA's lanes (T = 300 -> 320 threads, one waypoint per thread).
+// The minima over the 28 capsule pairs and the 40 capsule-cuboid tests are EXACT but cost only a few exact evaluations
+// per waypoint.  With m = distance of the two capsule midpoints (resp. of a midpoint to the cuboid) and
+// reach = half lengths + radii, m - reach is a lower bound of the capsule distance, so a pair whose lower bound is not
+// below a threshold `thr` known to be >= the PATH's minimum cannot supply that minimum.  The threshold comes from the
+// warp: every lane evaluates exactly the one pair that looks closest for its waypoint (smallest m^2 - reach^2, no
+// square root), and the minimum of these 32 exact distances over the warp's lanes (shuffles) is `thr` - the lanes of
+// a warp are consecutive waypoints of the same path, so it is usually within millimetres of the path's true minimum.
+// Phase 2 tests m^2 < (thr + reach)^2 for every pair from the midpoints in registers (fully unrolled, compile-time
+// reach) and runs the closed form only for the survivors - typically 0-2 of 68.  (The first version evaluated every
+// pair exactly unless its lower bound exceeded the THREAD's running minimum: 0.64 ms for 8192 x 300 waypoints, more
+// than the LM assembly itself.)
+template <class M, int BLOCK>
+__device__ __forceinline__ float self_min_distance(const float (&mid2)[M::NCAP][3], const float* sm, const CollTables<M>& tb) {
+    float dd[M::NPAIR];  // 4 x squared distance of the capsule midpoints
+    float key = INFINITY;
+    int cand = 0;
+    static_for<M::NPAIR>([&](auto Pp) {
+        constexpr int p = decltype(Pp)::value;
+        constexpr int a = pair_cap<M>(p, 0), b = pair_cap<M>(p, 1);
+        constexpr float lim = pair_reach<M>(p);
+        const float mx = mid2[a][0] - mid2[b][0], my = mid2[a][1] - mid2[b][1], mz = mid2[a][2] - mid2[b][2];
+        dd[p] = fmaf(mz, mz, fmaf(my, my, mx * mx));
+        const float kp = dd[p] - 4.f * lim * lim;
+        cand = kp < key ? p : cand;
+        key = fminf(key, kp);
+    });
+    float C2[3], nrm[3];
+    float d = self_pair_exact<M, BLOCK>(sm, tb, cand, C2, nrm);
+    const float thr = warp_min(d);  // >= the path's minimum: exact distances of 32 of its waypoints
+    unsigned mask = 0u;
+    static_for<M::NPAIR>([&](auto Pp) {
+        constexpr int p = decltype(Pp)::value;
+        const float lim = thr + pair_reach<M>(p);  // lower bound m - reach < thr  <=>  m < thr + reach
+        mask |= (lim > 0.f && dd[p] < 4.f * lim * lim) ? (1u << p) : 0u;
+    });
+    mask &= ~(1u << cand);
+    while (mask) {
+        const int p = __ffs(mask) - 1;
+        mask &= mask - 1;
+        d = fminf(d, self_pair_exact<M, BLOCK>(sm, tb, p, C2, nrm));
+    }
+    return d;
+}
+
+// 4 x squared distances of the NCAP capsule midpoints to cuboid o (the obstacle constants are hoisted out of the capsule loop)
+template <class M>
+__device__ __forceinline__ void env_midpoint_bounds(const float (&mid2)[M::NCAP][3], const Obstacles& ob, int o,
+                                                    float (&dd)[M::NCAP]) {
+    const float t2[3] = {2.f * ob.t[o][0], 2.f * ob.t[o][1], 2.f * ob.t[o][2]};
+    const float lo2[3] = {2.f * ob.lo[o][0], 2.f * ob.lo[o][1], 2.f * ob.lo[o][2]};
+    const float hi2[3] = {2.f * ob.hi[o][0], 2.f * ob.hi[o][1], 2.f * ob.hi[o][2]};
+    if (ob.has_rot[o]) {
+        static_for<M::NCAP>([&](auto Cc) {
+            constexpr int c = decltype(Cc)::value;
+            const float v[3] = {mid2[c][0] - t2[0], mid2[c][1] - t2[1], mid2[c][2] - t2[2]};
+            float acc = 0.f;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float m = fmaf(ob.R[o][6 + r], v[2], fmaf(ob.R[o][3 + r], v[1], ob.R[o][r] * v[0]));
+                const float e = m - fminf(fmaxf(m, lo2[r]), hi2[r]);
+                acc = fmaf(e, e, acc);
+            }
+            dd[c] = acc;
+        });
+    } else {
+        const float wlo[3] = {lo2[0] + t2[0], lo2[1] + t2[1], lo2[2] + t2[2]};
+        const float whi[3] = {hi2[0] + t2[0], hi2[1] + t2[1], hi2[2] + t2[2]};
+        static_for<M::NCAP>([&](auto Cc) {
+            constexpr int c = decltype(Cc)::value;
+            float acc = 0.f;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float e = mid2[c][r] - fminf(fmaxf(mid2[c][r], wlo[r]), whi[r]);
+                acc = fmaf(e, e, acc);
+            }
+            dd[c] = acc;
+        });
+    }
+}
+
+template <class M, int BLOCK>
+__device__ __forceinline__ float env_min_distance(const float (&mid2)[M::NCAP][3], const float* sm, const CollTables<M>& tb,
+                                                  const Obstacles& ob) {
+    if (ob.n == 0) return INFINITY;
+    // phase 1: the closest-looking (obstacle, capsule) test over ALL obstacles; one exact evaluation; warp threshold.
+    // The bounds of an obstacle are recomputed in phase 2 (12 instructions per test) rather than kept in 80 registers.
+    float key = INFINITY;
+    int cand = 0;
+    for (int o = 0; o < ob.n; ++o) {
+        float dd[M::NCAP];
+        env_midpoint_bounds<M>(mid2, ob, o, dd);
+        static_for<M::NCAP>([&](auto Cc) {
+            constexpr int c = decltype(Cc)::value;
+            constexpr float lim = cap_reach<M>(c);
+            const float kp = dd[c] - 4.f * lim * lim;
+            cand = kp < key ? o * 16 + c : cand;
+            key = fminf(key, kp);
+        });
+    }
+    float Cw[3], nrm[3];
+    float d = env_capsule_exact<M, BLOCK>(sm, tb, cand & 15, cand >> 4, Cw, nrm);
+    const float thr = warp_min(d);
+    for (int o = 0; o < ob.n; ++o) {
+        float dd[M::NCAP];
+        env_midpoint_bounds<M>(mid2, ob, o, dd);
+        unsigned mask = 0u;
+        static_for<M::NCAP>([&](auto Cc) {
+            constexpr int c = decltype(Cc)::value;
+            const float lim = thr + cap_reach<M>(c);
+            mask |= (lim > 0.f && dd[c] < 4.f * lim * lim) ? (1u << c) : 0u;
+        });
+        if (o == (cand >> 4)) mask &= ~(1u << (cand & 15));
+        while (mask) {
+            const int c = __ffs(mask) - 1;
+            mask &= mask - 1;
+            d = fminf(d, env_capsule_exact<M, BLOCK>(sm, tb, c, o, Cw, nrm));
+        }
+    }
+    return d;
+}
+
+template <class M, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+path_metrics_many_kernel(const float* __restrict__ q, const float* __restrict__ target, int64_t T, const Obstacles ob,
+                         float* __restrict__ out, float tag) {
+    constexpr int D = M::NDOF;
+    constexpr int NWARP = BLOCK / 32;
+    extern __shared__ float smem[];
+    __shared__ CollTables<M> tb;
+    __shared__ float red[7][NWARP];
+    fill_coll_tables<M>(tb, ob, threadIdx.x, BLOCK);
+    __syncthreads();
+    const int64_t p = blockIdx.x;
+    float* sm = smem + threadIdx.x;
+    float m_pos = 0.f, m_rot = 0.f, m_rev = 0.f, m_pri = 0.f, tl = 0.f, d_self = INFINITY, d_env = INFINITY;
+    for (int64_t t0 = 0; t0 < T; t0 += BLOCK) {
+        // every lane runs the body (the distance thresholds are shared through warp shuffles): lanes beyond the path
+        // shadow its last waypoint - maxima and minima do not mind the duplicate, the trajectory length skips it
+        const bool act = t0 + threadIdx.x < T;
+        const int64_t t = act ? t0 + threadIdx.x : T - 1;
+        const int64_t i = p * T + t;
+        float x[D];
+        load_q<M>(q, i, x);
+        MidSink<M, BLOCK, false> sink;
+        sink.sm = sm;
+        Frame F;
+        fk_chain<M>(x, sink, F);
+        const float* tg = target + t * 7;
+        const float dx = __ldg(tg) - F.p[0], dy = __ldg(tg + 1) - F.p[1], dz = __ldg(tg + 2) - F.p[2];
+        m_pos = fmaxf(m_pos, 100.f * sqrtf(dx * dx + dy * dy + dz * dz));
+        float qc[4];
+        rotmat_to_quat(F.R, qc);
+        float dot = fabsf(qc[0] * __ldg(tg + 3) + qc[1] * __ldg(tg + 4) + qc[2] * __ldg(tg + 5) + qc[3] * __ldg(tg + 6));
+        dot = fminf(dot, 1.f - 1e-7f);
+        m_rot = fmaxf(m_rot, 2.f * acosf(dot) * 57.29577951308232f);
+        if (t > 0) {
+            float xp[D];
+            load_q<M>(q, i - 1, xp);
+            static_for<D>([&](auto Dd) {
+                constexpr int d = decltype(Dd)::value;
+                if constexpr (dof_is_prismatic<M>(d)) {
+                    m_pri = fmaxf(m_pri, 100.f * fabsf(x[d] - xp[d]));
+                } else {
+                    const float w = fabsf(wrap_pi(x[d] - xp[d]));
+                    m_rev = fmaxf(m_rev, w * 57.29577951308232f);
+                    tl += act ? w : 0.f;
+                }
+            });
+        }
+        d_self = fminf(d_self, self_min_distance<M, BLOCK>(sink.mid2, sm, tb));
+        d_env = fminf(d_env, env_min_distance<M, BLOCK>(sink.mid2, sm, tb, ob));
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float v[7] = {warp_max(m_pos), warp_max(m_rot), warp_max(m_rev), warp_max(m_pri), warp_sum(tl), warp_min(d_self),
+                  warp_min(d_env)};
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) red[k][warp] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float r[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) r[k] = red[k][0];
+        for (int w = 1; w < NWARP; ++w) {
+            r[0] = fmaxf(r[0], red[0][w]); r[1] = fmaxf(r[1], red[1][w]);
+            r[2] = fmaxf(r[2], red[2][w]); r[3] = fmaxf(r[3], red[3][w]);
+            r[4] += red[4][w];
+            r[5] = fminf(r[5], red[5][w]); r[6] = fminf(r[6], red[6][w]);
+        }
+        float* o = out + p * 8;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) o[k] = r[k];
+        __threadfence_system();  // `out` may be host memory polled by the CPU: the tag must not overtake the metrics
+        *reinterpret_cast<volatile float*>(o + 7) = tag;
+    }
+}
+
+template <class M, int BLOCK>
+static int launch_metrics_many(const float* d_q, const float* d_target, int64_t P, int64_t T, const Obstacles& ob,
+                               float* d_out, float tag, cudaStream_t st) {
+    const size_t sh = sizeof(float) * BLOCK * SmemLayout<M>::N_DIST;
+    static SmemGrant granted;
+    if (int rc = ensure_dynamic_smem(path_metrics_many_kernel<M, BLOCK>, sh, granted)) return rc;
+    path_metrics_many_kernel<M, BLOCK><<<(unsigned)P, BLOCK, sh, st>>>(d_q, d_target, T, ob, d_out, tag);
+    return CPPFLOW_OK;
+}
+
 }  // namespace cppflow
 
 using namespace cppflow;
@@ -227,7 +439,21 @@ int cppflow::path_metrics_tagged(int robot, const float* d_q, const float* d_tar
                                      : cudaLaunchKernelEx(&cfg, path_metrics_kernel<M, true, 1>, d_q, d_target, T, ob, d_out, tag, PoseFuse{});
             if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "path_metrics cluster launch: %s", cudaGetErrorString(e));
         } else {
-            path_metrics_kernel<M, false, 1><<<(unsigned)P, MBLOCK, sh, (cudaStream_t)stream>>>(d_q, d_target, T, ob, d_out, tag, PoseFuse{});
+            // block size with the fewest idle lanes over the passes a path needs (ties: the larger block)
+            int best = 128;
+            int64_t waste = -1;
+            for (int b : {128, 192, 256, 320}) {
+                const int64_t w = (T + b - 1) / b * b - T;
+                if (waste < 0 || w <= waste) { waste = w; best = b; }
+            }
+            int rc = CPPFLOW_OK;
+            switch (best) {
+                case 128: rc = launch_metrics_many<M, 128>(d_q, d_target, P, T, ob, d_out, tag, (cudaStream_t)stream); break;
+                case 192: rc = launch_metrics_many<M, 192>(d_q, d_target, P, T, ob, d_out, tag, (cudaStream_t)stream); break;
+                case 256: rc = launch_metrics_many<M, 256>(d_q, d_target, P, T, ob, d_out, tag, (cudaStream_t)stream); break;
+                default: rc = launch_metrics_many<M, 320>(d_q, d_target, P, T, ob, d_out, tag, (cudaStream_t)stream); break;
+            }
+            if (rc) return rc;
         }
     });
     CPPFLOW_CHECK_LAUNCH();
