@@ -94,8 +94,10 @@ def make_params(pms) -> LmParamsC:
     for flag in ("pose_do_scale_down_satisfied", "differencing_do_ignore_satisfied", "differencing_do_scale_satisfied"):
         if getattr(pms, flag, False):
             raise NotImplementedError(
-                f"OptimizationParameters.{flag}=True is not used by the live parameter sets "
-                "(lm_hyper_parameters.py:86-151) and is not implemented by the CUDA path"
+                f"OptimizationParameters.{flag}=True: the row scaling / filtering options are implemented on the dense form "
+                "(optimization_utils.LmResidualFns.get_r_and_J and its helpers), not in the block-tridiagonal CUDA solver. "
+                "Both live parameter sets leave them off (lm_hyper_parameters.py:86-151) and the reference's own "
+                "get_r_and_J raises AttributeError when one is on (it reads pms.constraints, optimization_utils.py:515-520)"
             )
     return LmParamsC(
         f(pms.lm_lambda), f(pms.alpha_position), f(pms.alpha_rotation), f(pms.alpha_differencing),

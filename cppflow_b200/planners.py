@@ -3,8 +3,10 @@ PlannerSearcher :301-336, CppFlowPlanner.generate_plan :345-468).
 
 IKFlow (the conditional normalising flow that proposes the k candidate joint paths, planners.py:116-172) is out of
 scope - its pretrained weights are not available offline - so the candidate generator is a pluggable callable
-`(problem, k) -> [k, T, ndof]`.  The default, `LmIkCandidateGenerator`, draws k smooth random joint paths and pulls
-each waypoint onto the target pose with a few pose-only LM steps of the CUDA kernel."""
+`(problem, k) -> [k, T, ndof]`.  The default, `LatentIkCandidateGenerator`, keeps the reference's latent plumbing (one
+latent per path, tiled over the waypoints; sampling around the latent of an initial configuration) on top of
+`LatentIkSolver`, which traces one inverse-kinematics branch per latent by coarse-to-fine numerical continuation with
+the pose-only LM steps of the CUDA kernel."""
 from time import time
 from typing import Callable, Dict, Optional, Tuple
 
@@ -29,9 +31,8 @@ class LmIkCandidateGenerator:
     """k candidate paths = k random joint configurations, each copied to every waypoint and pulled onto that waypoint's
     target pose by pose-only LM steps of the CUDA kernel (csrc/k_pose.cu) with a decreasing damping schedule
     (lambda 1e-1 -> 1e-6: from a far seed the reference's lambda = 1e-6 is a Gauss-Newton step and converges on only
-    ~15-30 % of the waypoints in 6 steps; the damped schedule reaches 80-90 % on the 7-dof arms and makes the planner
-    return a valid plan on 12 of the 13 benchmark problems instead of 9).  A stand-in for IKFlow sampling, not a
-    reimplementation."""
+    ~15-30 % of the waypoints in 6 steps; the damped schedule reaches 80-90 % on the 7-dof arms).  Every waypoint is
+    solved on its own from the same far seed - the first stand-in; `LatentIkSolver` below replaces it."""
 
     LAMBDAS = (1e-1,) * 4 + (3e-2,) * 4 + (1e-2,) * 4 + (1e-3,) * 3 + (1e-4, 1e-5, 1e-6, 1e-6, 1e-6)
 
@@ -52,6 +53,242 @@ class LmIkCandidateGenerator:
         return x.reshape(k, T, robot.ndof)
 
 
+class LatentIkSolver:
+    """Stands where `IKFlowSolver` stands in the reference (planners.py:75-82, :165-171): a map
+    (end-effector pose path, latent) -> joint configurations in which ONE latent picks ONE smooth inverse-kinematics
+    branch along the whole path.  IKFlow gets that from a conditional normalising flow with pretrained weights (not
+    available offline); here the latent IS a seed configuration in normalised joint coordinates (`network_width` =
+    ndof, latent 0 = the middle of every joint range, +-1 = +-60 % of the half range), and the branch is traced by
+    numerical continuation on the CUDA pose-step kernel (csrc/k_pose.cu), coarse to fine:
+
+      1. waypoint 0 of every path: damped LM steps from the seed (lambda 1e-1 -> 1e-6, the far-seed schedule);
+      2. every `stride`-th waypoint in sequence, each started from the previous coarse waypoint's solution;
+      3. the gaps are halved level by level: a new waypoint starts from the joint-space interpolation of its two solved
+         neighbours (all new waypoints of a level in ONE launch) and takes a few lightly damped steps;
+      4. two undamped polishing steps over all k * T waypoints.
+
+    Solving every waypoint independently from the same far seed (the first stand-in, `LmIkCandidateGenerator`) reached
+    the target on ~30 % of the Fetch waypoints and the branches of neighbouring waypoints did not match; continuation
+    converges wherever the branch exists and gives dp_search paths that are already smooth."""
+
+    FAR = (1e-1,) * 4 + (3e-2,) * 4 + (1e-2,) * 4 + (1e-3,) * 3 + (1e-4, 1e-5, 1e-6, 1e-6, 1e-6)
+    NEAR = (1e-2, 1e-3, 1e-3, 1e-4, 1e-5, 1e-6, 1e-6, 1e-6)
+    FILL = (1e-4, 1e-5, 1e-6, 1e-6)
+    POLISH = (1e-6, 1e-6)
+    LATENT_TO_HALF_RANGE = 0.6
+
+    def __init__(self, robot, stride: int = 16):
+        self.robot = robot
+        self.network_width = robot.ndof
+        self.stride = max(1, int(stride))
+        self._prm = ops.make_params(ALT_LOSS_V2_1_POSE)
+        lim = torch.tensor(robot.actuated_joints_limits, dtype=torch.float32)
+        self._mid, self._half = lim.mean(dim=1), (lim[:, 1] - lim[:, 0]) / 2
+        self._schedules: Dict = {}
+        self.last_converged: Optional[torch.Tensor] = None
+
+    # latent <-> seed configuration (the role of the flow's forward / reverse pass, planners.py:174-189)
+    def latent_to_configuration(self, latent: torch.Tensor) -> torch.Tensor:
+        mid, half = self._mid.to(latent.device), self._half.to(latent.device)
+        return mid + self.LATENT_TO_HALF_RANGE * half * latent.clamp(-1.0 / self.LATENT_TO_HALF_RANGE, 1.0 / self.LATENT_TO_HALF_RANGE)
+
+    def configuration_to_latent(self, q: torch.Tensor) -> torch.Tensor:
+        mid, half = self._mid.to(q.device), self._half.to(q.device)
+        return (q - mid) / (self.LATENT_TO_HALF_RANGE * half)
+
+    def _steps(self, x: torch.Tensor, targets: torch.Tensor, lambdas) -> torch.Tensor:
+        return ops.lm_pose_steps_(self.robot.robot_id, self.robot.ndof, self._prm, lambdas, x, targets, True)
+
+    def _schedule(self, T: int, dev):
+        """Coarse waypoints and, per refinement level, (new waypoints, left / right solved neighbours, interpolation
+        weights) as device index tensors - built once per (T, device)."""
+        key = (T, str(dev))
+        if key not in self._schedules:
+            coarse = list(range(0, T, self.stride))
+            if coarse[-1] != T - 1:
+                coarse.append(T - 1)
+            solved, levels = list(coarse), []
+            while True:
+                new, left, right = [], [], []
+                for a, b in zip(solved[:-1], solved[1:]):
+                    if b - a > 1:
+                        new.append((a + b) // 2); left.append(a); right.append(b)
+                if not new:
+                    break
+                ni, li, ri = (torch.tensor(v, device=dev) for v in (new, left, right))
+                levels.append((ni, li, ri, ((ni - li).float() / (ri - li).float())[None, :, None]))
+                solved = sorted(solved + new)
+            self._schedules[key] = (coarse, levels)
+        return self._schedules[key]
+
+    def _converged(self, x: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        """bool [n]: pose error inside the plan constraints (0.1 mm, 0.1 deg; scripts/evaluate.py:51-56)"""
+        err, _ = ops.pose_errors(self.robot.robot_id, self.robot.ndof, x, targets)
+        return (err[:, 3:].norm(dim=1) < 1e-4) & (err[:, :3].norm(dim=1) < 1.745e-3)
+
+    def solve_paths(self, ee_path: torch.Tensor, latents: torch.Tensor, generator: Optional[torch.Generator] = None,
+                    n_restarts: int = 3) -> torch.Tensor:
+        """ee_path [T, 7], latents [k, network_width] -> [k, T, ndof]; `self.last_converged` = bool [k, T].
+        Nothing here synchronises with the host."""
+        T, k, D = ee_path.shape[0], latents.shape[0], self.robot.ndof
+        dev = ee_path.device
+        ee_path = ee_path.contiguous()
+        x = torch.empty((k, T, D), device=dev, dtype=torch.float32)
+        cur = self.latent_to_configuration(latents.to(dev).float()).contiguous()
+        self._steps(cur, ee_path[0:1], self.FAR)
+        # a damped LM descent with joint-limit clamping gets stuck on ~40 % of random Fetch seeds: the seeds that did
+        # not reach the first pose are redrawn (the converged ones keep their latent's branch)
+        for _ in range(n_restarts):
+            ok = self._converged(cur, ee_path[0:1])
+            fresh = torch.rand((k, self.network_width), generator=generator) * 2 - 1
+            alt = self.latent_to_configuration(fresh.to(dev)).contiguous()
+            self._steps(alt, ee_path[0:1], self.FAR)
+            cur = torch.where(ok[:, None], cur, alt)
+        x[:, 0] = cur
+        coarse, levels = self._schedule(T, dev)
+        for t in coarse[1:]:
+            cur = cur.clone()
+            self._steps(cur, ee_path[t:t + 1], self.NEAR)
+            # a branch that ended (joint limit, singularity) restarts from a fresh seed at this waypoint; if that fails
+            # too it is continued on a converged path's branch, drawn at random
+            ok = self._converged(cur, ee_path[t:t + 1])
+            fresh = torch.rand((k, self.network_width), generator=generator) * 2 - 1
+            alt = self.latent_to_configuration(fresh.to(dev)).contiguous()
+            self._steps(alt, ee_path[t:t + 1], self.FAR)
+            ok_alt = self._converged(alt, ee_path[t:t + 1])
+            cur = torch.where(ok[:, None], cur, alt)
+            ok = ok | ok_alt
+            donor = torch.multinomial(ok.float() + 1e-9, k, replacement=True)
+            cur = torch.where(ok[:, None], cur, cur[donor])
+            x[:, t] = cur
+        for ni, li, ri, w in levels:
+            sub = (x[:, li] * (1 - w) + x[:, ri] * w).reshape(k * ni.numel(), D).contiguous()
+            self._steps(sub, ee_path[ni].contiguous(), self.FILL)
+            x[:, ni] = sub.reshape(k, ni.numel(), D)
+        flat = x.reshape(k * T, D)
+        self._steps(flat, ee_path, self.POLISH)
+        self.last_converged = self._converged(flat, ee_path).reshape(k, T)
+        return flat.reshape(k, T, D)
+
+    def generate_ik_solutions(self, ee_path_tiled: torch.Tensor, latent: torch.Tensor, clamp_to_joint_limits: bool = True):
+        """IKFlowSolver.generate_ik_solutions' call shape (planners.py:165-171): ee_path_tiled [k*T, 7] = the pose path
+        repeated k times, latent [k*T, width] = one latent per path repeated T times (`_sample_latents`) -> [k*T, ndof].
+        The joint-limit clamp is part of every LM step, so `clamp_to_joint_limits` is always in force."""
+        assert ee_path_tiled.shape[0] == latent.shape[0]
+        n = latent.shape[0]
+        # rows of one path share their latent: the first change of latent marks T
+        T = n if n < 2 else int((latent[1:] != latent[:-1]).any(dim=1).nonzero()[0, 0]) + 1 if bool((latent[1:] != latent[:-1]).any()) else n
+        assert n % T == 0
+        k = n // T
+        return self.solve_paths(ee_path_tiled[:T], latent.reshape(k, T, -1)[:, 0]).reshape(n, self.robot.ndof)
+
+
+class LatentIkCandidateGenerator:
+    """`(problem, k) -> [k, T, ndof]` through the reference's latent plumbing (planners.py:116-172, :191-216): one
+    latent per path (`_sample_latents`, uniform or gaussian with `latent_vector_scale`, tiled over the T waypoints as
+    [k*T, width]), sampled around the latent of `problem.initial_configuration` when there is one
+    (`_get_configuration_corresponding_latent` + `_sample_latents_near`, whose first path keeps the centre latent)."""
+
+    def __init__(self, seed: int = 0, latent_distribution: str = "uniform", latent_vector_scale: float = 2.0, stride: int = 16,
+                 clearance_steps: int = 4, clearance_m: float = 0.02, clearance_alpha: float = 0.5):
+        """`clearance_steps` batched all-terms LM steps over the k candidate paths with a collision weight of
+        `clearance_alpha` against cuboids inflated by `clearance_m` push candidates that graze an obstacle (or
+        themselves) clear of it through their null-space motion, followed by two pose-only steps that restore the pose
+        to full precision.  IKFlow's samples need no such step; branches traced by continuation know nothing of the
+        obstacles, and on the tight problems (panda__flappy_bird: a 20 cm gap between two pillars) not one of 175 of them
+        is collision-free from end to end.  0 switches the stage off."""
+        assert latent_distribution in {"uniform", "gaussian"}
+        self.gen = torch.Generator().manual_seed(seed)
+        self.latent_distribution, self.latent_vector_scale, self.stride = latent_distribution, latent_vector_scale, stride
+        self.clearance_steps, self.clearance_m, self.clearance_alpha = clearance_steps, clearance_m, clearance_alpha
+        self._solvers: Dict[str, LatentIkSolver] = {}
+        self.last_converged: Optional[torch.Tensor] = None  # bool [k, T] of the last call: pose reached per waypoint
+
+    def solver(self, robot) -> LatentIkSolver:
+        if robot.name not in self._solvers:
+            self._solvers[robot.name] = LatentIkSolver(robot, self.stride)
+        return self._solvers[robot.name]
+
+    def _sample_latents(self, k: int, n_timesteps: int, width: int) -> torch.Tensor:
+        """planners.py:116-134"""
+        if self.latent_distribution == "gaussian":
+            latents = torch.randn((k, width), generator=self.gen) * self.latent_vector_scale
+        else:
+            w = self.latent_vector_scale
+            latents = torch.rand((k, width), generator=self.gen) * w - (w / 2)
+        return torch.repeat_interleave(latents, n_timesteps, dim=0)
+
+    def _sample_latents_near(self, k: int, n_timesteps: int, center_latent: torch.Tensor) -> torch.Tensor:
+        """planners.py:136-153"""
+        width = center_latent.numel()
+        w = self.latent_vector_scale
+        latents = torch.rand((k, width), generator=self.gen) * w - (w / 2) + center_latent.reshape(1, width).cpu()
+        latents[0] = center_latent.reshape(width).cpu()
+        return torch.repeat_interleave(latents, n_timesteps, dim=0)
+
+    def _get_configuration_corresponding_latent(self, robot, qs: torch.Tensor, ee_pose: torch.Tensor) -> torch.Tensor:
+        """planners.py:174-189 (the flow run in reverse): here the latent of a configuration is the configuration itself
+        in normalised joint coordinates; the pose it reaches plays no role."""
+        return self.solver(robot).configuration_to_latent(qs.reshape(1, robot.ndof).float().cpu())
+
+    def _get_k_ikflow_qpaths(self, robot, ee_path: torch.Tensor, batched_latent: torch.Tensor, k: int) -> torch.Tensor:
+        """planners.py:155-172 -> stacked [k, T, ndof]"""
+        n = ee_path.shape[0]
+        assert batched_latent.shape[0] == k * n, "one latent row per (path, waypoint), as _sample_latents lays them out"
+        # == generate_ik_solutions(ee_path.repeat((k, 1)), batched_latent) without materialising the tiled pose path
+        solver = self.solver(robot)
+        qs = solver.solve_paths(ee_path, batched_latent.reshape(k, n, -1)[:, 0], generator=self.gen)
+        self.last_converged = solver.last_converged
+        return qs
+
+    def _clear_obstacles(self, problem: Problem, qs: torch.Tensor) -> torch.Tensor:
+        from dataclasses import replace
+
+        from .lm_hyper_parameters import all_terms_parameters
+
+        robot, (k, T, D) = problem.robot, qs.shape
+        if self.clearance_steps <= 0 or T < 2:
+            return qs
+        m = self.clearance_m
+        grow = torch.tensor([-m, -m, -m, m, m, m])
+        ob = ops.Obstacles([c.detach().cpu() + grow for c in (problem.obstacles_cuboids or [])],
+                           [t.detach().cpu() for t in (problem.obstacles_Tcuboids or [])])
+        prm = ops.make_params(replace(all_terms_parameters(), use_virtual_configs=False, lm_lambda=1e-4,
+                                      alpha_self_collision=self.clearance_alpha, alpha_env_collision=self.clearance_alpha))
+        x = qs.reshape(k * T, D)
+        for _ in range(self.clearance_steps):
+            x = ops.lm_full_step(robot.robot_id, D, prm, x, None, problem.target_path, k, T, ob, True)
+        solver = self.solver(robot)
+        solver._steps(x, problem.target_path, solver.POLISH)
+        # waypoints that reach the pose AND keep `clearance_m` from every cuboid are the ones dp_search should prefer: the
+        # differencing steps of the LM loop pull a path that hugs an obstacle straight into it
+        _, near = ops.collision_flags(robot.robot_id, D, x, ob, want_self=False) if ob.n else (None, None)
+        ok = solver._converged(x, problem.target_path)
+        self.last_converged = (ok if near is None else ok & ~near.bool()).reshape(k, T)
+        return x.reshape(k, T, D)
+
+    def __call__(self, problem: Problem, k: int, initial_q_latent: Optional[torch.Tensor] = None) -> torch.Tensor:
+        robot, T = problem.robot, problem.n_timesteps
+        if problem.initial_configuration is not None and initial_q_latent is None:
+            initial_q_latent = self._get_configuration_corresponding_latent(robot, problem.initial_configuration,
+                                                                            problem.target_path[0])
+        if initial_q_latent is not None:
+            batched = self._sample_latents_near(k, T, initial_q_latent)
+        else:
+            batched = self._sample_latents(k, T, robot.ndof)
+        return self._clear_obstacles(problem, self._get_k_ikflow_qpaths(robot, problem.target_path, batched, k))
+
+
+def _with_unreached_waypoints(env_v: torch.Tensor, generator) -> torch.Tensor:
+    """IKFlow's samples all lie close to the target pose; the stand-in generator's do not where its LM descent got
+    stuck.  Such waypoints (generator.last_converged == False) are handed to dp_search as violations (the K_COLLISION_COST
+    penalty of search.py:15), so the search prefers candidates that actually reach the pose - it cannot see pose errors."""
+    conv = getattr(generator, "last_converged", None)
+    if conv is None or conv.shape != env_v.shape:
+        return env_v
+    return env_v | ~conv
+
+
 def report_from_qpath(qpath: torch.Tensor, problem: Problem) -> PathReport:
     """Capsule-based stand-in for plan_from_qpath (data_type_utils.py:244-276; its klampt mesh checks are out of scope)."""
     m = path_metrics(problem, qpath.contiguous(), 1).cpu()[0].tolist()
@@ -65,7 +302,7 @@ class Planner:
     def __init__(self, settings: PlannerSettings, robot, candidate_generator: Optional[CandidateGenerator] = None):
         self._cfg = settings
         self._robot = robot
-        self._candidates = candidate_generator if candidate_generator is not None else LmIkCandidateGenerator()
+        self._candidates = candidate_generator if candidate_generator is not None else LatentIkCandidateGenerator()
 
     def set_settings(self, settings: PlannerSettings):
         self._cfg = settings
@@ -92,6 +329,7 @@ class Planner:
         k_current = qs.shape[0]
         self_v, env_v = qpaths_batched_collisions(problem, qs)  # one launch for both flag sets
         pct = torch.stack([self_v.sum(), env_v.sum()]).float().cpu() / (k_current * problem.n_timesteps) * 100  # one sync
+        env_v = _with_unreached_waypoints(env_v, self._candidates)
         assert pct[0] < 95.0, f"too many self collisions: {pct[0]} %"
         assert pct[1] < 95.0, f"too many env collisions: {pct[1]} %"
         if existing_q_data is not None:
@@ -237,6 +475,7 @@ def plan_many(planner_factory: Callable[[Problem], Planner], problems):
             qs = pl._candidates(p, pl._cfg.k)
             self_v, env_v = qpaths_batched_collisions(p, qs)
             counts = torch.stack([self_v.sum(), env_v.sum()]).float()
+            env_v = _with_unreached_waypoints(env_v, pl._candidates)
             if p.initial_configuration is not None:
                 qs[:, 0, :] = p.initial_configuration.to(qs.device)
                 self_v[:, 0] = False

@@ -50,6 +50,20 @@ class LmParams:
     use_self_collisions: bool = True
     use_env_collisions: bool = True
     virtual_configs: Optional[torch.Tensor] = None
+    # row scaling / filtering options (off in both live parameter sets; lm_hyper_parameters.py:30-45).  The reference's
+    # get_r_and_J reads the thresholds from `pms.constraints` (optimization_utils.py:515-520, :562-567) - a field its
+    # OptimizationParameters does not have, so it cannot reach these branches today; here `constraints` is the tuple
+    # (max_allowed_position_error_cm, max_allowed_rotation_error_deg, max_allowed_mjac_deg, max_allowed_mjac_cm).
+    pose_do_scale_down_satisfied: bool = False
+    pose_ignore_satisfied_threshold_scale: float = 1.0
+    pose_ignore_satisfied_scale_down: float = 0.5
+    differencing_do_ignore_satisfied: bool = False
+    differencing_ignore_satisfied_margin_deg: float = 0.0
+    differencing_ignore_satisfied_margin_cm: float = 0.0
+    differencing_do_scale_satisfied: bool = False
+    differencing_scale_down_satisfied_scale: float = 0.5
+    differencing_scale_down_satisfied_shift_invalid_to_threshold: bool = False
+    constraints: Optional[Tuple[float, float, float, float]] = None
 
 
 # lm_hyper_parameters.py:86-118
@@ -122,6 +136,71 @@ def _row_masks(model: RobotModel, n_rows: int):
     return revolute, torch.logical_not(revolute)
 
 
+def _rotation_and_position_row_mask(n: int):
+    """optimization_utils.py:239-250: rows [rot, rot, rot, pos, pos, pos] per waypoint"""
+    rotation = torch.zeros(6, dtype=torch.bool)
+    rotation[:3] = True
+    rotation = rotation.tile(n)
+    return rotation, torch.logical_not(rotation)
+
+
+def scale_down_rows_pose_below_error(r: torch.Tensor, J: torch.Tensor, error_threshold_m: float, error_threshold_rad: float,
+                                     scale: float):
+    """LmResidualFns._scale_down_rows_from_r_J_pose_below_error (optimization_utils.py:288-329, without its untested
+    shift option): rows whose |error| is below the threshold of their kind are multiplied by `scale`, in place.
+    -> (r, J, invalid_row_idxs)"""
+    assert r.shape[0] == J.shape[0] and r.shape[0] % 6 == 0 and 0.0 <= scale < 1.0
+    rotation_rows, position_rows = _rotation_and_position_row_mask(r.numel() // 6)
+    do_rot = torch.logical_and(r[:, 0].abs() < error_threshold_rad, rotation_rows)
+    do_pos = torch.logical_and(r[:, 0].abs() < error_threshold_m, position_rows)
+    r[do_pos, :] *= scale
+    r[do_rot, :] *= scale
+    J[do_pos, :] *= scale
+    J[do_rot, :] *= scale
+    return r, J, torch.logical_not(torch.logical_or(do_rot, do_pos))
+
+
+def scale_down_rows_differencing_below_error(model: RobotModel, r: torch.Tensor, J: torch.Tensor, mjac_threshold_m: float,
+                                             mjac_threshold_rad: float, scale: float,
+                                             shift_invalid_to_threshold: bool = False):
+    """LmResidualFns._scale_down_rows_from_r_J_differencing_below_error (optimization_utils.py:352-397), in place.
+    -> (J, r, invalid_row_idxs)  [the reference returns J first]"""
+    assert 0.0 <= scale < 1.0 and r.shape[0] % model.ndof == 0
+    revolute_rows, prismatic_rows = _row_masks(model, r.numel())
+    below_m = r[:, 0].abs() < mjac_threshold_m
+    below_rad = r[:, 0].abs() < mjac_threshold_rad
+    valid_pri = torch.logical_and(below_m, prismatic_rows)
+    invalid_pri = torch.logical_and(torch.logical_not(below_m), prismatic_rows)
+    valid_rev = torch.logical_and(below_rad, revolute_rows)
+    invalid_rev = torch.logical_and(torch.logical_not(below_rad), revolute_rows)
+    r[valid_pri, :] *= scale
+    r[valid_rev, :] *= scale
+    J[valid_pri, :] *= scale
+    J[valid_rev, :] *= scale
+    if shift_invalid_to_threshold:
+        r[torch.logical_and((r < -mjac_threshold_rad)[:, 0], invalid_rev)] += mjac_threshold_rad
+        r[torch.logical_and((r > mjac_threshold_rad)[:, 0], invalid_rev)] -= mjac_threshold_rad
+        r[torch.logical_and((r < -mjac_threshold_m)[:, 0], invalid_pri)] += mjac_threshold_m
+        r[torch.logical_and((r > mjac_threshold_m)[:, 0], invalid_pri)] -= mjac_threshold_m
+    return J, r, torch.logical_not(torch.logical_or(valid_pri, valid_rev))
+
+
+def filter_rows_from_r_J_differencing(model: RobotModel, r: torch.Tensor, J: torch.Tensor, threshold_rad: float,
+                                      threshold_m: float, shift_to_threshold: bool = True):
+    """optimization_utils.py:736-768: keep only the rows whose |residual| exceeds the threshold of their joint type,
+    optionally moved towards zero by the threshold."""
+    assert r.shape[0] == J.shape[0] and r.shape[0] % model.ndof == 0
+    revolute_idxs, prismatic_idxs = _row_masks(model, r.shape[0])
+    keep = torch.logical_or(torch.logical_and(r.abs()[:, 0] > threshold_rad, revolute_idxs),
+                            torch.logical_and(r.abs()[:, 0] > threshold_m, prismatic_idxs))
+    if shift_to_threshold:
+        r[torch.logical_and((r < -threshold_rad)[:, 0], revolute_idxs)] += threshold_rad
+        r[torch.logical_and((r > threshold_rad)[:, 0], revolute_idxs)] -= threshold_rad
+        r[torch.logical_and((r < -threshold_m)[:, 0], prismatic_idxs)] += threshold_m
+        r[torch.logical_and((r > threshold_m)[:, 0], prismatic_idxs)] -= threshold_m
+    return r[keep, :], J[keep, :]
+
+
 def get_r_and_J(pms: LmParams, model: RobotModel, x: torch.Tensor, target_path: torch.Tensor,
                 Tcuboids: Optional[List] = None, cuboids: Optional[List] = None):
     """optimization_utils.py:486-731.  Returns dicts of the per-term dense residuals / Jacobians (None when the
@@ -138,10 +217,11 @@ def get_r_and_J(pms: LmParams, model: RobotModel, x: torch.Tensor, target_path: 
             Jp[6 * i : 6 * i + 6, i * ndof : (i + 1) * ndof] = J_fk[i]
         pose_errors, _ = get_6d_pose_errors(model, x, target_path)
         rp = pose_errors.flatten()[:, None].clone()
-        rot_rows = torch.zeros(6, dtype=torch.bool)
-        rot_rows[:3] = True
-        rot_rows = rot_rows.tile(n)
-        pos_rows = torch.logical_not(rot_rows)
+        if pms.pose_do_scale_down_satisfied:  # :513-531 (threshold units as in the reference: m and "deg" taken as rad)
+            thr_m = pms.pose_ignore_satisfied_threshold_scale * pms.constraints[0] / 100
+            thr_rad = pms.pose_ignore_satisfied_threshold_scale * pms.constraints[1]
+            rp, Jp, _ = scale_down_rows_pose_below_error(rp, Jp, thr_m, thr_rad, pms.pose_ignore_satisfied_scale_down)
+        rot_rows, pos_rows = _rotation_and_position_row_mask(n)
         rp[rot_rows, :] *= pms.alpha_rotation
         rp[pos_rows, :] *= pms.alpha_position
         Jp[rot_rows, :] *= pms.alpha_rotation
@@ -153,7 +233,17 @@ def get_r_and_J(pms: LmParams, model: RobotModel, x: torch.Tensor, target_path: 
         zeros = torch.zeros((ndof * (n - 1), ndof * n), dtype=dt)
         Jd = torch.diagonal_scatter(zeros, torch.ones(ndof * (n - 1), dtype=dt), 0)
         Jd = torch.diagonal_scatter(Jd, -torch.ones(ndof * (n - 1), dtype=dt), offset=ndof)
-        if model.has_prismatic_joints:
+        assert not (pms.differencing_do_scale_satisfied and pms.differencing_do_ignore_satisfied), "use one or the other"
+        if pms.differencing_do_ignore_satisfied or pms.differencing_do_scale_satisfied:  # :560-567
+            thr_rad = float(np.deg2rad(pms.constraints[2] - pms.differencing_ignore_satisfied_margin_deg))
+            thr_m = (pms.constraints[3] - pms.differencing_ignore_satisfied_margin_cm) / 100
+        if pms.differencing_do_ignore_satisfied:  # :570-578
+            rd, Jd = filter_rows_from_r_J_differencing(model, rd, Jd, thr_rad, thr_m, shift_to_threshold=True)
+        if pms.differencing_do_scale_satisfied:  # :581-593
+            Jd, rd, _ = scale_down_rows_differencing_below_error(
+                model, rd, Jd, thr_m, thr_rad, pms.differencing_scale_down_satisfied_scale,
+                pms.differencing_scale_down_satisfied_shift_invalid_to_threshold)
+        if model.has_prismatic_joints and not pms.differencing_do_ignore_satisfied:  # :606-609
             _, pris_rows = _row_masks(model, rd.shape[0])
             rd[pris_rows] *= pms.alpha_differencing_prismatic_scaling
             Jd[pris_rows] *= pms.alpha_differencing_prismatic_scaling

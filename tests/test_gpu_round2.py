@@ -338,3 +338,37 @@ def test_dp_search_long_path_takes_the_single_cta_sweep(robots):
     best, memo, costs, chosen = ops.dp_search(rob.robot_id, rob.ndof, q.to(DEV), sv.to(DEV), ev.to(DEV))
     ref_best, ref_memo, ref_costs, ref_chosen = S.dp_search(m, q, sv, ev)
     assert torch.equal(memo.cpu(), ref_memo) and torch.equal(costs.cpu(), ref_costs) and torch.equal(best.cpu(), ref_best)
+
+
+@pytest.fixture(scope="module")
+def rowscale_golden():
+    import os
+
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_rowscale_golden.npz"))
+
+
+def test_row_scaling_helpers_vs_golden(robots, rowscale_golden):
+    """The host mirror of the reference's row scaling / filtering helpers (device tensors, torch ops) against the
+    reference's own outputs (SURVEY 8c golden items 4-6)."""
+    from cppflow_b200.optimization_utils import LmResidualFns, filter_rows_from_r_J_differencing
+
+    g = rowscale_golden
+    for key in ("fetch/unit", "fetch/random", "panda/random"):
+        rob = robots[str(g[f"{key}/robot"])]
+        for shift in (0, 1):
+            r, J = torch.tensor(g[f"{key}/diff/r_in"]).to(DEV), torch.tensor(g[f"{key}/diff/J_in"]).to(DEV)
+            Jo, ro, inv = LmResidualFns._scale_down_rows_from_r_J_differencing_below_error(
+                rob, r, J, mjac_threshold_m=0.25, mjac_threshold_rad=1.5, scale=0.5, shift_invalid_to_threshold=bool(shift))
+            assert np.array_equal(ro.cpu().numpy(), g[f"{key}/diff/scale_shift{shift}/r"])
+            assert np.array_equal(Jo.cpu().numpy(), g[f"{key}/diff/scale_shift{shift}/J"])
+            assert np.array_equal(inv.cpu().numpy(), g[f"{key}/diff/scale_shift{shift}/invalid"])
+            r, J = torch.tensor(g[f"{key}/diff/r_in"]).to(DEV), torch.tensor(g[f"{key}/diff/J_in"]).to(DEV)
+            rf, Jf = filter_rows_from_r_J_differencing(rob, r, J, threshold_rad=1.5, threshold_m=0.25, shift_to_threshold=bool(shift))
+            assert np.array_equal(rf.cpu().numpy(), g[f"{key}/diff/filter_shift{shift}/r"])
+            assert np.array_equal(Jf.cpu().numpy(), g[f"{key}/diff/filter_shift{shift}/J"])
+    for key in ("pose/a", "pose/b"):
+        r, J = torch.tensor(g[f"{key}/r_in"]).to(DEV), torch.tensor(g[f"{key}/J_in"]).to(DEV)
+        ro, Jo, inv = LmResidualFns._scale_down_rows_from_r_J_pose_below_error(r, J, error_threshold_m=0.01,
+                                                                               error_threshold_rad=0.03, scale=0.25)
+        assert np.array_equal(ro.cpu().numpy(), g[f"{key}/r"]) and np.array_equal(Jo.cpu().numpy(), g[f"{key}/J"])
+        assert np.array_equal(inv.cpu().numpy(), g[f"{key}/invalid"])

@@ -271,3 +271,67 @@ def test_alternating_loop_matches_reference_loop(loop_golden, case, dt_name):
         np.testing.assert_allclose(x.numpy(), g[f"{key}/x_opt"], atol=1e-6 if dt_name == "f32" else 1e-12)
     # the golden set covers: valid after the first pose steps, convergence exit, never valid
     assert bool(g["fetch_smooth/normal/f32/is_valid"]) and not bool(g["fetch_colliding/anytime/f32/is_valid"])
+
+
+@pytest.fixture(scope="module")
+def rowscale_golden():
+    import os
+
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_rowscale_golden.npz"))
+
+
+@pytest.mark.parametrize("key", ["fetch/unit", "fetch/random", "panda/random"])
+def test_differencing_row_scaling_and_filtering(rowscale_golden, key):
+    """SURVEY 8c golden items 4 and 6: _scale_down_rows_from_r_J_differencing_below_error (optimization_utils.py:352-397)
+    and filter_rows_from_r_J_differencing (:736-768), with and without the shift, against the reference's outputs;
+    `fetch/unit` is the input of the reference's own test (tests/optimization_utils_test.py:126-155)."""
+    g = rowscale_golden
+    m = R.get_model(str(g[f"{key}/robot"]))
+    for shift in (0, 1):
+        J, r, inv = L.scale_down_rows_differencing_below_error(m, T(g[f"{key}/diff/r_in"]), T(g[f"{key}/diff/J_in"]), 0.25, 1.5,
+                                                               0.5, bool(shift))
+        assert np.array_equal(r.numpy(), g[f"{key}/diff/scale_shift{shift}/r"])
+        assert np.array_equal(J.numpy(), g[f"{key}/diff/scale_shift{shift}/J"])
+        assert np.array_equal(inv.numpy(), g[f"{key}/diff/scale_shift{shift}/invalid"])
+        r, J = L.filter_rows_from_r_J_differencing(m, T(g[f"{key}/diff/r_in"]), T(g[f"{key}/diff/J_in"]), 1.5, 0.25, bool(shift))
+        assert np.array_equal(r.numpy(), g[f"{key}/diff/filter_shift{shift}/r"])
+        assert np.array_equal(J.numpy(), g[f"{key}/diff/filter_shift{shift}/J"])
+    if key == "fetch/unit":  # the expected values spelled out in the reference's test (:137-186)
+        _, r, inv = L.scale_down_rows_differencing_below_error(m, T(g[f"{key}/diff/r_in"]), T(g[f"{key}/diff/J_in"]), 0.25, 1.5, 0.5)
+        assert inv.nonzero()[:, 0].tolist() == [0, 2, 8, 9, 10]
+        assert r[:, 0].tolist() == pytest.approx([0.5, 0.05, 1.6] + [0.05] * 5 + [-0.4, 1.7, -1.7] + [0.05] * 5 + [0.1, 0.005] + [0.05] * 6)
+
+
+@pytest.mark.parametrize("key", ["pose/a", "pose/b"])
+def test_pose_row_scaling(rowscale_golden, key):
+    """SURVEY 8c golden item 5: _scale_down_rows_from_r_J_pose_below_error (optimization_utils.py:288-329)."""
+    g = rowscale_golden
+    r, J, inv = L.scale_down_rows_pose_below_error(T(g[f"{key}/r_in"]), T(g[f"{key}/J_in"]), 0.01, 0.03, 0.25)
+    assert np.array_equal(r.numpy(), g[f"{key}/r"]) and np.array_equal(J.numpy(), g[f"{key}/J"])
+    assert np.array_equal(inv.numpy(), g[f"{key}/invalid"])
+    assert 0 < int(inv.sum()) < inv.numel()
+
+
+def test_row_scaling_options_in_dense_get_r_and_J():
+    """The options change the dense system the way the reference's get_r_and_J composes them: scaled rows before the
+    alpha factors, filtered differencing rows dropped (and no prismatic scaling then, optimization_utils.py:606)."""
+    from dataclasses import replace
+
+    m = R.get_model("fetch")
+    g = torch.Generator().manual_seed(3)
+    x = torch.tensor(np.asarray(m.actuated_joints_limits)).float().mean(dim=1)[None] + 0.2 * torch.randn((12, 8), generator=g)
+    target = K.forward_kinematics(m, x.double() + 0.01).float()
+    base = L.LmParams(use_pose=True, use_virtual_configs=False, use_self_collisions=False, use_env_collisions=False,
+                      alpha_differencing_prismatic_scaling=2.0, constraints=(0.01, 0.1, 7.0, 2.0))
+    J0, r0 = L.get_r_and_J(base, m, x, target)
+    J1, r1 = L.get_r_and_J(replace(base, differencing_do_scale_satisfied=True, differencing_ignore_satisfied_margin_deg=1.0,
+                                   differencing_ignore_satisfied_margin_cm=0.5), m, x, target)
+    small = (r0["differencing"].abs() < 1e-9) | (r1["differencing"].abs() <= r0["differencing"].abs() + 1e-12)
+    assert small.all() and not torch.equal(r0["differencing"], r1["differencing"])
+    J2, r2 = L.get_r_and_J(replace(base, differencing_do_ignore_satisfied=True, differencing_ignore_satisfied_margin_deg=1.0,
+                                   differencing_ignore_satisfied_margin_cm=0.5), m, x, target)
+    assert 0 < r2["differencing"].shape[0] < r0["differencing"].shape[0] and J2["differencing"].shape[0] == r2["differencing"].shape[0]
+    J3, r3 = L.get_r_and_J(replace(base, pose_do_scale_down_satisfied=True, pose_ignore_satisfied_threshold_scale=500.0,
+                                   pose_ignore_satisfied_scale_down=0.5), m, x, target)
+    ratio = r3["pose"] / r0["pose"]
+    assert set(np.round(ratio[torch.isfinite(ratio)].numpy(), 4).tolist()) <= {0.5, 1.0} and (ratio == 0.5).any()
