@@ -127,3 +127,31 @@ def problem_from_filename(constraints: Optional[Constraints], problem_filename: 
 
 def get_all_problems(device=None) -> List[Problem]:
     return [problem_from_filename(None, name, device=device) for name in ALL_PROBLEM_FILENAMES]
+
+
+def plan_from_qpath(qpath: torch.Tensor, problem: Problem):
+    """data_type_utils.py:244-276: FK, per-timestep errors and collision flags of a joint-space path -> Plan.
+    The reference asks klampt's mesh checker for the per-timestep collisions ("a tighter bound" than the capsules, :252);
+    klampt is out of scope, so the flags are the capsule kernels' (d < 0 for any pair / capsule-cuboid test)."""
+    from .collision_detection import qpaths_batched_collisions
+    from .data_types import Plan
+    from .evaluation_utils import positional_errors, rotational_errors
+
+    assert isinstance(qpath, torch.Tensor), f"qpath must be a torch.Tensor, got {type(qpath)}"
+    robot = problem.robot
+    traced_path = robot.forward_kinematics(qpath)
+    qpath_revolute, qpath_prismatic = robot.split_configs_to_revolute_and_prismatic(qpath)
+    self_colliding, env_colliding = qpaths_batched_collisions(problem, qpath[None].contiguous())
+    self_colliding, env_colliding = self_colliding[0], env_colliding[0]
+    if config.SELF_COLLISIONS_IGNORED:
+        self_colliding = torch.zeros_like(self_colliding)
+    if config.ENV_COLLISIONS_IGNORED:
+        env_colliding = torch.zeros_like(env_colliding)
+    return Plan(
+        q_path=qpath, q_path_revolute=qpath_revolute, q_path_prismatic=qpath_prismatic, pose_path=traced_path,
+        target_path=problem.target_path, robot_joint_limits=robot.actuated_joints_limits,
+        self_colliding_per_ts=self_colliding, env_colliding_per_ts=env_colliding,
+        positional_errors=positional_errors(traced_path, problem.target_path),
+        rotational_errors=rotational_errors(traced_path, problem.target_path),
+        provided_initial_configuration=problem.initial_configuration, constraints=problem.constraints,
+    )

@@ -77,3 +77,33 @@ def errors_are_below_threshold(max_allowed_position_error_cm, max_allowed_rotati
                 print("errors_are_below_threshold() |", txt)
     return (pose_pos_valid and pose_rot_valid and mjac_rev_valid and mjac_pris_valid,
             (pose_pos_valid, pose_rot_valid, mjac_rev_valid, mjac_pris_valid))
+
+
+# ======================
+#   ==  Pose error  ==
+#
+
+
+def geodesic_distance_between_quaternions(q1: torch.Tensor, q2: torch.Tensor) -> torch.Tensor:
+    """jrl.math_utils.geodesic_distance_between_quaternions (quoted at data_types.py:408-411): 2 acos(dot) with the
+    1e-7 clamp, folded into [0, pi] so that q and -q are the same rotation."""
+    acos_clamp_epsilon = 1e-7
+    dot = torch.clip(torch.sum(q1 * q2, dim=1), -1, 1)
+    distance = 2 * torch.acos(torch.clamp(dot, -1 + acos_clamp_epsilon, 1 - acos_clamp_epsilon))
+    return torch.abs(torch.remainder(distance + torch.pi, 2 * torch.pi) - torch.pi)
+
+
+def positional_errors(path_1: torch.Tensor, path_2: torch.Tensor) -> torch.Tensor:
+    """evaluation_utils.py:131-133"""
+    return torch.norm(path_1[:, :3] - path_2[:, :3], dim=1)
+
+
+def rotational_errors(path_1: torch.Tensor, path_2: torch.Tensor) -> torch.Tensor:
+    """evaluation_utils.py:136-138"""
+    return geodesic_distance_between_quaternions(path_1[:, 3:], path_2[:, 3:])
+
+
+def calculate_pose_error_cm_deg(robot, x: torch.Tensor, target_path: torch.Tensor):
+    """evaluation_utils.py:113-117: per-configuration positional (cm) and rotational (deg) errors; FK on the GPU."""
+    traced_path = robot.forward_kinematics(x)
+    return 100 * positional_errors(target_path, traced_path), torch.rad2deg(rotational_errors(target_path, traced_path))

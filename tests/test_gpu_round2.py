@@ -372,3 +372,35 @@ def test_row_scaling_helpers_vs_golden(robots, rowscale_golden):
                                                                                error_threshold_rad=0.03, scale=0.25)
         assert np.array_equal(ro.cpu().numpy(), g[f"{key}/r"]) and np.array_equal(Jo.cpu().numpy(), g[f"{key}/J"])
         assert np.array_equal(inv.cpu().numpy(), g[f"{key}/invalid"])
+
+
+@pytest.mark.parametrize("name", ["fetch__circle", "panda__1cube"])
+def test_plan_from_qpath(name):
+    """plan_from_qpath (data_type_utils.py:244-276) on the GPU: the Plan's derived metrics agree with the fast PathReport
+    of the same path and with the fp64 oracle; its per-timestep collision flags are the capsule kernels'."""
+    from cppflow_b200.collision_detection import qpaths_batched_collisions
+    from cppflow_b200.data_type_utils import plan_from_qpath, problem_from_filename
+    from cppflow_b200.data_types import PlanNp
+    from cppflow_b200.planners import LatentIkCandidateGenerator, report_from_qpath
+
+    problem = problem_from_filename(None, name, device=DEV)
+    rob = problem.robot
+    m = R.get_model(rob.name)
+    qs = LatentIkCandidateGenerator(seed=4)(problem, 8)
+    for q in (qs[0].contiguous(), qs[3].contiguous()):
+        plan = plan_from_qpath(q, problem)
+        rep = report_from_qpath(q, problem)
+        cuboids = [c.cpu().double() for c in problem.obstacles_cuboids]
+        Tcuboids = [t.cpu().double() for t in problem.obstacles_Tcuboids]
+        ref = L.path_metrics(m, q.cpu().double(), problem.target_path.cpu().double(), Tcuboids, cuboids)
+        assert plan.q_path.shape == (problem.n_timesteps, rob.ndof) and plan.pose_path.shape == (problem.n_timesteps, 7)
+        assert abs(plan.max_positional_error_cm - float(ref["max_pos_cm"])) < 2e-3
+        assert abs(plan.max_positional_error_cm - rep.max_positional_error_cm) < 1e-4
+        assert abs(plan.mjac_deg - float(ref["mjac_deg"])) < 1e-3 and abs(plan.mjac_cm - float(ref["mjac_cm"])) < 1e-4
+        assert abs(plan.path_length_rad - float(ref["tl"])) < 1e-4 * max(1.0, float(ref["tl"]))
+        assert abs(plan.path_length_rad - rep.path_length_rad) < 1e-4 * max(1.0, rep.path_length_rad)
+        sv, ev = qpaths_batched_collisions(problem, q[None].contiguous())
+        assert torch.equal(plan.self_colliding_per_ts, sv[0]) and torch.equal(plan.env_colliding_per_ts, ev[0])
+        assert bool(plan.env_colliding_per_ts.any()) == (float(ref["min_env"]) < 0)
+        assert plan.is_valid == rep.is_valid
+        assert isinstance(PlanNp(plan).q_path, np.ndarray)

@@ -1,5 +1,6 @@
 """CPU: host-side logic that does not need a GPU - parameter marshalling, validity decisions, problem loading,
 sharding, and the multi-rank cost gather over gloo (world_size 2)."""
+import math
 import os
 import socket
 
@@ -214,3 +215,67 @@ def test_numa_local_is_a_safe_no_op_without_topology():
     with numa_local("cuda:0"):
         pass
     assert os.sched_getaffinity(0) == before
+
+
+def test_plan_metrics_match_the_reference_definitions():
+    """Plan (data_types.py:86-348) on CPU tensors: derived metrics, validity and the numpy view."""
+    from cppflow_b200.data_types import Plan, PlanNp, Constraints
+    from cppflow_b200.evaluation_utils import positional_errors, rotational_errors
+    from oracle import robots as OR, kinematics as OK, lm as OL
+
+    m = OR.get_model("fetch")
+    lim = torch.tensor(m.actuated_joints_limits)
+    g = torch.Generator().manual_seed(0)
+    T = 20
+    q = lim.mean(dim=1)[None] + 0.02 * torch.randn((T, 8), generator=g).cumsum(dim=0)
+    target = OK.forward_kinematics(m, q.double()).float()
+    q2 = q.clone()
+    q2[7] += 0.004  # a pose error of a few mm and a joint jump
+    traced = OK.forward_kinematics(m, q2.double()).float()
+    plan = Plan(q_path=q2, q_path_revolute=q2[:, m.revolute_joint_idxs], q_path_prismatic=q2[:, m.prismatic_joint_idxs],
+                pose_path=traced, target_path=target, robot_joint_limits=m.actuated_joints_limits,
+                self_colliding_per_ts=torch.zeros(T, dtype=torch.bool), env_colliding_per_ts=torch.zeros(T, dtype=torch.bool),
+                positional_errors=positional_errors(traced, target), rotational_errors=rotational_errors(traced, target),
+                provided_initial_configuration=None, constraints=Constraints(0.01, 0.1, 7.0, 2.0))
+    ref = OL.path_metrics(m, q2.double(), target.double())
+    assert plan.max_positional_error_cm == pytest.approx(float(ref["max_pos_cm"]), abs=1e-4)
+    assert plan.max_positional_error_mm == pytest.approx(10 * plan.max_positional_error_cm)
+    assert plan.max_rotational_error_deg == pytest.approx(float(ref["max_rot_deg"]), abs=3e-2)
+    assert plan.mjac_deg == pytest.approx(float(ref["mjac_deg"]), abs=1e-4)
+    assert plan.mjac_cm == pytest.approx(float(ref["mjac_cm"]), abs=1e-4)
+    assert plan.path_length_rad == pytest.approx(float(ref["tl"]), rel=1e-5)
+    assert plan.path_length_m == pytest.approx(float((q2[1:, 0] - q2[:-1, 0]).abs().sum()), rel=1e-5)
+    assert plan.is_a_prismatic_joint and not plan.joint_limits_violated and plan.initial_q_norm_dist == 0.0
+    assert plan.is_valid is False and "errors_are_below_threshold(...): False" in plan.is_valid_(verbose=True)[1]
+    assert "max positional error" in str(plan)
+    assert isinstance(PlanNp(plan).positional_errors, np.ndarray) and PlanNp(plan).mjac_deg == plan.mjac_deg
+    exact = Plan(q_path=q, q_path_revolute=q[:, m.revolute_joint_idxs], q_path_prismatic=q[:, m.prismatic_joint_idxs],
+                 pose_path=target, target_path=target, robot_joint_limits=m.actuated_joints_limits,
+                 self_colliding_per_ts=torch.zeros(T, dtype=torch.bool), env_colliding_per_ts=torch.zeros(T, dtype=torch.bool),
+                 positional_errors=positional_errors(target, target), rotational_errors=rotational_errors(target, target),
+                 provided_initial_configuration=q[0:1] + 0.5, constraints=Constraints(0.01, 0.1, 7.0, 2.0))
+    assert exact.max_rotational_error_deg == pytest.approx(math.degrees(2 * math.acos(1 - 1e-7)), abs=1e-2)  # the clamp floor (0.056 in fp32)
+    assert exact.is_valid is False  # too far from the requested initial configuration (0.5 * sqrt(8) > 0.2)
+    exact.provided_initial_configuration = q[0:1]
+    assert exact.is_valid is True
+    colliding = exact
+    colliding.env_colliding_per_ts = colliding.env_colliding_per_ts.clone()
+    colliding.env_colliding_per_ts[3] = True
+    assert colliding.is_valid is False
+
+
+def test_problem_rotational_path_length_discounts_the_clamp_floor():
+    """data_types.py:403-418: identical consecutive orientations contribute 0, not 2 acos(1 - 1e-7)."""
+    from cppflow_b200.data_types import Problem
+
+    T = 10
+    target = torch.zeros((T, 7))
+    target[:, 3] = 1.0
+    target[:, 0] = torch.linspace(0, 0.09, T)
+    p = Problem(DEFAULT_CONSTRAINTS, target, None, _FakeRobot(), "line", "fake__line", [], [], [], [])
+    assert p.path_length_cumultive_positional_change_cm == pytest.approx(9.0, abs=1e-4)
+    assert abs(p.path_length_cumulative_rotational_change_deg) < 1e-3
+    half = math.sin(math.radians(5.0))
+    target[5:, 3], target[5:, 6] = math.cos(math.radians(5.0)), half  # one 10 degree turn about z
+    p = Problem(DEFAULT_CONSTRAINTS, target, None, _FakeRobot(), "line", "fake__line", [], [], [], [])
+    assert p.path_length_cumulative_rotational_change_deg == pytest.approx(10.0, abs=2e-2)
