@@ -227,7 +227,9 @@ def test_plan_metrics_match_the_reference_definitions():
     lim = torch.tensor(m.actuated_joints_limits)
     g = torch.Generator().manual_seed(0)
     T = 20
-    q = lim.mean(dim=1)[None] + 0.02 * torch.randn((T, 8), generator=g).cumsum(dim=0)
+    steps = 0.02 * torch.randn((T, 8), generator=g)
+    steps[:, 0] *= 0.2  # the prismatic torso: millimetres per waypoint
+    q = lim.mean(dim=1)[None] + steps.cumsum(dim=0)
     target = OK.forward_kinematics(m, q.double()).float()
     q2 = q.clone()
     q2[7] += 0.004  # a pose error of a few mm and a joint jump
