@@ -96,28 +96,9 @@ class LatentIkSolver:
         mid, half = self._mid.to(q.device), self._half.to(q.device)
         return (q - mid) / (self.LATENT_TO_HALF_RANGE * half)
 
-    def _steps(self, x: torch.Tensor, targets: torch.Tensor, lambdas, k: Optional[int] = None, aware=None) -> torch.Tensor:
-        """len(lambdas) LM steps in place on x [n, ndof] (row i tracks targets[i % len(targets)]).  Pose-only steps of
-        the pose kernel by default; with `aware` = (Obstacles, alpha) the steps also carry the capsule self- and
-        env-collision rows with weight alpha (levenberg_marquardt_full with pose + collision terms, no differencing:
-        x is read as k independent paths of n / k waypoints), so a branch is traced AROUND the obstacles where the arm's
-        null-space motion allows it."""
-        if aware is None:
-            return ops.lm_pose_steps_(self.robot.robot_id, self.robot.ndof, self._prm, lambdas, x, targets, True)
-        from dataclasses import replace
-
-        from .lm_hyper_parameters import all_terms_parameters
-
-        ob, alpha = aware
-        n = x.shape[0]
-        P = k if k is not None else n // targets.shape[0]
-        T = n // P
-        assert P * T == n and targets.shape[0] == T
-        for lam in lambdas:
-            prm = ops.make_params(replace(all_terms_parameters(), use_virtual_configs=False, use_differencing=False,
-                                          lm_lambda=lam, alpha_self_collision=alpha, alpha_env_collision=alpha))
-            x.copy_(ops.lm_full_step(self.robot.robot_id, self.robot.ndof, prm, x, None, targets, P, T, ob, True))
-        return x
+    def _steps(self, x: torch.Tensor, targets: torch.Tensor, lambdas) -> torch.Tensor:
+        """len(lambdas) pose-only LM steps in place on x [n, ndof]; row i tracks targets[i % len(targets)]"""
+        return ops.lm_pose_steps_(self.robot.robot_id, self.robot.ndof, self._prm, lambdas, x, targets, True)
 
     def _schedule(self, T: int, dev):
         """Coarse waypoints and, per refinement level, (new waypoints, left / right solved neighbours, interpolation
@@ -147,43 +128,46 @@ class LatentIkSolver:
         return (err[:, 3:].norm(dim=1) < 1e-4) & (err[:, :3].norm(dim=1) < 1.745e-3)
 
     def solve_paths(self, ee_path: torch.Tensor, latents: torch.Tensor, generator: Optional[torch.Generator] = None,
-                    n_restarts: int = 3, aware=None) -> torch.Tensor:
+                    n_restarts: int = 3) -> torch.Tensor:
         """ee_path [T, 7], latents [k, network_width] -> [k, T, ndof]; `self.last_converged` = bool [k, T].
         Nothing here synchronises with the host."""
         T, k, D = ee_path.shape[0], latents.shape[0], self.robot.ndof
         dev = ee_path.device
         ee_path = ee_path.contiguous()
         x = torch.empty((k, T, D), device=dev, dtype=torch.float32)
+        coarse, levels = self._schedule(T, dev)
+        # every random number of the call in ONE host -> device copy: fresh seeds for the restarts at waypoint 0 and at
+        # every coarse waypoint (a per-waypoint copy from pageable memory would serialise host and device each time)
+        fresh = (torch.rand((n_restarts + len(coarse) - 1, k, self.network_width), generator=generator) * 2 - 1).to(dev)
+        alts = self.latent_to_configuration(fresh)
         cur = self.latent_to_configuration(latents.to(dev).float()).contiguous()
         self._steps(cur, ee_path[0:1], self.FAR)
         # a damped LM descent with joint-limit clamping gets stuck on ~40 % of random Fetch seeds: the seeds that did
         # not reach the first pose are redrawn (the converged ones keep their latent's branch)
-        for _ in range(n_restarts):
+        for r in range(n_restarts):
             ok = self._converged(cur, ee_path[0:1])
-            fresh = torch.rand((k, self.network_width), generator=generator) * 2 - 1
-            alt = self.latent_to_configuration(fresh.to(dev)).contiguous()
+            alt = alts[r].contiguous()
             self._steps(alt, ee_path[0:1], self.FAR)
             cur = torch.where(ok[:, None], cur, alt)
         x[:, 0] = cur
-        coarse, levels = self._schedule(T, dev)
-        for t in coarse[1:]:
+        for j, t in enumerate(coarse[1:]):
             cur = cur.clone()
-            self._steps(cur, ee_path[t:t + 1], self.NEAR, aware=aware)
+            self._steps(cur, ee_path[t:t + 1], self.NEAR)
             # a branch that ended (joint limit, singularity) restarts from a fresh seed at this waypoint; if that fails
-            # too it is continued on a converged path's branch, drawn at random
+            # too it is continued on a converged path's branch, drawn at random (per path: the argmax of a random score
+            # over the converged paths)
             ok = self._converged(cur, ee_path[t:t + 1])
-            fresh = torch.rand((k, self.network_width), generator=generator) * 2 - 1
-            alt = self.latent_to_configuration(fresh.to(dev)).contiguous()
+            alt = alts[n_restarts + j].contiguous()
             self._steps(alt, ee_path[t:t + 1], self.FAR)
             ok_alt = self._converged(alt, ee_path[t:t + 1])
             cur = torch.where(ok[:, None], cur, alt)
             ok = ok | ok_alt
-            donor = torch.multinomial(ok.float() + 1e-9, k, replacement=True)
+            donor = (torch.rand((k, k), device=dev) * ok[None, :]).argmax(dim=1)
             cur = torch.where(ok[:, None], cur, cur[donor])
             x[:, t] = cur
         for ni, li, ri, w in levels:
             sub = (x[:, li] * (1 - w) + x[:, ri] * w).reshape(k * ni.numel(), D).contiguous()
-            self._steps(sub, ee_path[ni].contiguous(), self.FILL, k=k, aware=aware)
+            self._steps(sub, ee_path[ni].contiguous(), self.FILL)
             x[:, ni] = sub.reshape(k, ni.numel(), D)
         flat = x.reshape(k * T, D)
         self._steps(flat, ee_path, self.POLISH)
@@ -209,20 +193,10 @@ class LatentIkCandidateGenerator:
     [k*T, width]), sampled around the latent of `problem.initial_configuration` when there is one
     (`_get_configuration_corresponding_latent` + `_sample_latents_near`, whose first path keeps the centre latent)."""
 
-    def __init__(self, seed: int = 0, latent_distribution: str = "uniform", latent_vector_scale: float = 2.0, stride: int = 16,
-                 clearance_steps: int = 0, clearance_m: float = 0.02, clearance_alpha: float = 0.5,
-                 clearance_min_fraction: float = 0.15, obstacle_aware: bool = False):
-        """`clearance_steps` batched all-terms LM steps over the k candidate paths with a collision weight of
-        `clearance_alpha` against cuboids inflated by `clearance_m` push candidates that graze an obstacle (or
-        themselves) clear of it through their null-space motion, followed by two pose-only steps that restore the pose
-        to full precision.  IKFlow's samples need no such step; branches traced by continuation know nothing of the
-        obstacles, and on the tight problems (panda__flappy_bird: a 20 cm gap between two pillars) not one of 175 of them
-        is collision-free from end to end.  0 switches the stage off."""
+    def __init__(self, seed: int = 0, latent_distribution: str = "uniform", latent_vector_scale: float = 2.0, stride: int = 16):
         assert latent_distribution in {"uniform", "gaussian"}
         self.gen = torch.Generator().manual_seed(seed)
         self.latent_distribution, self.latent_vector_scale, self.stride = latent_distribution, latent_vector_scale, stride
-        self.clearance_steps, self.clearance_m, self.clearance_alpha = clearance_steps, clearance_m, clearance_alpha
-        self.clearance_min_fraction, self.obstacle_aware = clearance_min_fraction, obstacle_aware
         self._solvers: Dict[str, LatentIkSolver] = {}
         self.last_converged: Optional[torch.Tensor] = None  # bool [k, T] of the last call: pose reached per waypoint
 
@@ -253,47 +227,15 @@ class LatentIkCandidateGenerator:
         in normalised joint coordinates; the pose it reaches plays no role."""
         return self.solver(robot).configuration_to_latent(qs.reshape(1, robot.ndof).float().cpu())
 
-    def _get_k_ikflow_qpaths(self, robot, ee_path: torch.Tensor, batched_latent: torch.Tensor, k: int, aware=None) -> torch.Tensor:
+    def _get_k_ikflow_qpaths(self, robot, ee_path: torch.Tensor, batched_latent: torch.Tensor, k: int) -> torch.Tensor:
         """planners.py:155-172 -> stacked [k, T, ndof]"""
         n = ee_path.shape[0]
         assert batched_latent.shape[0] == k * n, "one latent row per (path, waypoint), as _sample_latents lays them out"
         # == generate_ik_solutions(ee_path.repeat((k, 1)), batched_latent) without materialising the tiled pose path
         solver = self.solver(robot)
-        qs = solver.solve_paths(ee_path, batched_latent.reshape(k, n, -1)[:, 0], generator=self.gen, aware=aware)
+        qs = solver.solve_paths(ee_path, batched_latent.reshape(k, n, -1)[:, 0], generator=self.gen)
         self.last_converged = solver.last_converged
         return qs
-
-    def _clear_obstacles(self, problem: Problem, qs: torch.Tensor) -> torch.Tensor:
-        from dataclasses import replace
-
-        from .lm_hyper_parameters import all_terms_parameters
-
-        robot, (k, T, D) = problem.robot, qs.shape
-        n_ob = len(problem.obstacles_cuboids or [])
-        if n_ob == 0 or T < 2 or self.clearance_m <= 0:
-            return qs
-        m = self.clearance_m
-        grow = torch.tensor([-m, -m, -m, m, m, m])
-        ob = ops.Obstacles([c.detach().cpu() + grow for c in problem.obstacles_cuboids],
-                           [t.detach().cpu() for t in problem.obstacles_Tcuboids])
-        x = qs.reshape(k * T, D)
-        solver = self.solver(robot)
-        if self.clearance_steps > 0:
-            prm = ops.make_params(replace(all_terms_parameters(), use_virtual_configs=False, lm_lambda=1e-4,
-                                          alpha_self_collision=self.clearance_alpha, alpha_env_collision=self.clearance_alpha))
-            for _ in range(self.clearance_steps):
-                x = ops.lm_full_step(robot.robot_id, D, prm, x, None, problem.target_path, k, T, ob, True)
-            solver._steps(x, problem.target_path, solver.POLISH)
-        # dp_search cannot see clearances, only flags, and the differencing steps of the LM loop pull a path that grazes
-        # a cuboid ~1 cm into it (panda__flappy_bird never recovers from that).  Waypoints closer than `clearance_m` to a
-        # cuboid are therefore handed to the search as "not preferred" - but only at the waypoints where enough
-        # candidates keep the clearance, so that the search is never forced to trade a flag for a 180 degree jump.
-        ok = solver._converged(x, problem.target_path).reshape(k, T)
-        _, near = ops.collision_flags(robot.robot_id, D, x, ob, want_self=False)
-        near = near.bool().reshape(k, T)
-        enough = (ok & ~near).float().mean(dim=0) >= self.clearance_min_fraction  # [T]
-        self.last_converged = ok & ~(near & enough[None, :])
-        return x.reshape(k, T, D)
 
     def __call__(self, problem: Problem, k: int, initial_q_latent: Optional[torch.Tensor] = None) -> torch.Tensor:
         robot, T = problem.robot, problem.n_timesteps
@@ -304,16 +246,7 @@ class LatentIkCandidateGenerator:
             batched = self._sample_latents_near(k, T, initial_q_latent)
         else:
             batched = self._sample_latents(k, T, robot.ndof)
-        aware = None
-        if self.obstacle_aware and len(problem.obstacles_cuboids or []) > 0 and self.clearance_m > 0:
-            aware = (self._inflated(problem), self.clearance_alpha)
-        return self._clear_obstacles(problem, self._get_k_ikflow_qpaths(robot, problem.target_path, batched, k, aware))
-
-    def _inflated(self, problem: Problem):
-        m = self.clearance_m
-        grow = torch.tensor([-m, -m, -m, m, m, m])
-        return ops.Obstacles([c.detach().cpu() + grow for c in problem.obstacles_cuboids],
-                             [t.detach().cpu() for t in problem.obstacles_Tcuboids])
+        return self._get_k_ikflow_qpaths(robot, problem.target_path, batched, k)
 
 
 def _with_unreached_waypoints(env_v: torch.Tensor, generator) -> torch.Tensor:

@@ -8,9 +8,8 @@ from cppflow_b200.optimization_utils import path_metrics
 from cppflow_b200.search import dp_search
 from cppflow_b200.planners import LmIkCandidateGenerator, LatentIkCandidateGenerator
 dev = torch.device("cuda:0")
-gens = {"s16 no clearance": lambda: LatentIkCandidateGenerator(seed=1, clearance_steps=0),
-        "s16 clearance 4": lambda: LatentIkCandidateGenerator(seed=1),
-        "s16 clearance 4 m3": lambda: LatentIkCandidateGenerator(seed=1, clearance_m=0.03)}
+gens = {"latent stride 16": lambda: LatentIkCandidateGenerator(seed=1),
+        "latent stride 8": lambda: LatentIkCandidateGenerator(seed=1, stride=8)}
 tot = {g: [0, 0.0, 0.0] for g in gens}
 for name in ALL_PROBLEM_FILENAMES:
     problem = problem_from_filename(None, name, device=dev); rob = problem.robot; T = problem.n_timesteps

@@ -4,10 +4,8 @@ from cppflow_b200.data_type_utils import problem_from_filename, ALL_PROBLEM_FILE
 from cppflow_b200.data_types import PlannerSettings
 from cppflow_b200.planners import CppFlowPlanner, LatentIkCandidateGenerator, LmIkCandidateGenerator
 dev = torch.device("cuda:0")
-for label, kw, gen in (("aware a.5 m2", dict(do_rerun_if_large_dp_search_mjac=True), lambda s: LatentIkCandidateGenerator(seed=s, obstacle_aware=True)),
-                       ("aware a.2 m2", dict(do_rerun_if_large_dp_search_mjac=True), lambda s: LatentIkCandidateGenerator(seed=s, obstacle_aware=True, clearance_alpha=0.2)),
-                       ("aware a.5 m3", dict(do_rerun_if_large_dp_search_mjac=True), lambda s: LatentIkCandidateGenerator(seed=s, obstacle_aware=True, clearance_m=0.03)),
-                       ("aware a1 m2 no rerun", dict(), lambda s: LatentIkCandidateGenerator(seed=s, obstacle_aware=True, clearance_alpha=1.0))):
+for label, kw, gen in (("rerun on large mjac", dict(do_rerun_if_large_dp_search_mjac=True), lambda s: LatentIkCandidateGenerator(seed=s)),
+                       ("no rerun", dict(), lambda s: LatentIkCandidateGenerator(seed=s))):
     for seed in (1, 2, 3, 4):
         nv, bad, t_tot = 0, [], 0.0
         for name in ALL_PROBLEM_FILENAMES:
