@@ -24,6 +24,10 @@ __host__ __device__ constexpr float cap_half_length(int c) {
 }
 // slack added to every culling bound so that fp32 rounding can never cull a pair whose distance is < threshold
 #define CPPFLOW_CULL_MARGIN 1e-4f
+// A capsule axis that passes through (or touches) a cuboid has no outward normal: the oracle returns a zero gradient
+// when the axis-cuboid distance is <= 1e-12 in fp64.  In fp32 the closest point lands on a face plane up to rounding
+// (|diff| ~ 1e-8), so the same rule needs a threshold above that noise: 1 micrometre.
+#define CPPFLOW_AXIS_INSIDE_D2 1e-12f
 
 template <class M>
 struct PairTable {
@@ -209,7 +213,7 @@ __device__ __forceinline__ float env_capsule_distance(const float* sm, int c, co
     }
     const float d2 = dot3(diff, diff);
     const float dist = sqrtf(d2);
-    const float inv = d2 > 1e-24f ? rsqrtf(d2) : 0.f;
+    const float inv = d2 > CPPFLOW_AXIS_INSIDE_D2 ? rsqrtf(d2) : 0.f;
     float nb[3] = {diff[0] * inv, diff[1] * inv, diff[2] * inv};
     if (ob.has_rot[o]) {
 #pragma unroll
@@ -362,39 +366,51 @@ __host__ __device__ constexpr int n_static_capsules() {
 static_assert(n_static_capsules<Fetch>() == 1 && n_static_capsules<FetchArm>() == 2 && n_static_capsules<Panda>() == 1,
               "base link (and the fixed torso of fetch_arm) are the static capsules");
 
-// bit c set <=> capsule c may touch obstacle o; capsules below FIRST are not tested
+// bit c set <=> capsule c may touch obstacle o; capsules below FIRST are not tested.
+// Per axis the (doubled) distance of the capsule midpoint to the cuboid is max(|m - centre| - half extent, 0), evaluated
+// as ONE saturating add (FADD.SAT with the |.| source modifier): 3 FMA-pipe instructions per axis and none on the
+// half-rate ALU pipe, against FMNMX + FMNMX + FADD + FFMA for m - clamp(m, lo, hi).  Saturation at 1 is harmless where
+// the capsule's threshold is below 1 (an axis that saturates culls the pair, as its true value would); the few capsules
+// with a larger reach (a robot's base) take max(., 0) instead.
+template <bool SAT>
+__device__ __forceinline__ float positive_part(float x) {
+    if constexpr (SAT) return __saturatef(x);
+    else return fmaxf(x, 0.f);
+}
 template <class M, int FIRST = 0>
 __device__ __forceinline__ unsigned env_cull_mask(const float (&mid2)[M::NCAP][3], const Obstacles& ob, int o) {
     unsigned mask = 0u;
     const float t2[3] = {2.f * ob.t[o][0], 2.f * ob.t[o][1], 2.f * ob.t[o][2]};
-    const float lo2[3] = {2.f * ob.lo[o][0], 2.f * ob.lo[o][1], 2.f * ob.lo[o][2]};
-    const float hi2[3] = {2.f * ob.hi[o][0], 2.f * ob.hi[o][1], 2.f * ob.hi[o][2]};
+    // doubled centre / half extent of the cuboid in its own frame
+    const float cb[3] = {ob.lo[o][0] + ob.hi[o][0], ob.lo[o][1] + ob.hi[o][1], ob.lo[o][2] + ob.hi[o][2]};
+    const float hb[3] = {ob.hi[o][0] - ob.lo[o][0], ob.hi[o][1] - ob.lo[o][1], ob.hi[o][2] - ob.lo[o][2]};
     if (ob.has_rot[o]) {
         static_for<M::NCAP - FIRST>([&](auto Cc) {
             constexpr int c = decltype(Cc)::value + FIRST;
             constexpr float lim = cap_reach<M>(c);
             constexpr float lim2x4 = 4.f * lim * lim;
+            constexpr bool SAT = lim2x4 < 1.f;
             const float v[3] = {mid2[c][0] - t2[0], mid2[c][1] - t2[1], mid2[c][2] - t2[2]};
             float dd = 0.f;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const float m = fmaf(ob.R[o][6 + r], v[2], fmaf(ob.R[o][3 + r], v[1], ob.R[o][r] * v[0]));
-                const float e = m - fminf(fmaxf(m, lo2[r]), hi2[r]);
+                const float e = positive_part<SAT>(fabsf(m - cb[r]) - hb[r]);
                 dd = fmaf(e, e, dd);
             }
             mask |= (dd > lim2x4) ? 0u : (1u << c);
         });
     } else {
-        const float wlo[3] = {lo2[0] + t2[0], lo2[1] + t2[1], lo2[2] + t2[2]};
-        const float whi[3] = {hi2[0] + t2[0], hi2[1] + t2[1], hi2[2] + t2[2]};
+        const float cw[3] = {cb[0] + t2[0], cb[1] + t2[1], cb[2] + t2[2]};
         static_for<M::NCAP - FIRST>([&](auto Cc) {
             constexpr int c = decltype(Cc)::value + FIRST;
             constexpr float lim = cap_reach<M>(c);
             constexpr float lim2x4 = 4.f * lim * lim;
+            constexpr bool SAT = lim2x4 < 1.f;
             float dd = 0.f;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                const float e = mid2[c][r] - fminf(fmaxf(mid2[c][r], wlo[r]), whi[r]);
+                const float e = positive_part<SAT>(fabsf(mid2[c][r] - cw[r]) - hb[r]);
                 dd = fmaf(e, e, dd);
             }
             mask |= (dd > lim2x4) ? 0u : (1u << c);
@@ -475,7 +491,7 @@ __device__ __forceinline__ float env_capsule_exact(const float* sm, const CollTa
     }
     const float d2 = dot3(diff, diff);
     const float dist = sqrtf(d2);
-    const float inv = d2 > 1e-24f ? rsqrtf(d2) : 0.f;
+    const float inv = d2 > CPPFLOW_AXIS_INSIDE_D2 ? rsqrtf(d2) : 0.f;
     const float nb[3] = {diff[0] * inv, diff[1] * inv, diff[2] * inv};
     if (ob.has_rot[o]) {
 #pragma unroll

@@ -173,17 +173,19 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
         }
     }
     if (prm.use_env) {
-        // survivors of up to three obstacles share one 32-bit mask (bit = oo * NCAP + c) so that the lanes of a warp
-        // walk lists of similar length.  Capsules on links that no joint moves have a zero distance gradient: an
-        // active one adds nothing to (A, b), so they are not tested at all.
-        constexpr int OGRP = 32 / M::NCAP;
+        // survivors of up to seven obstacles share one 64-bit mask (bit = oo * NCAP + c): a warp pays the LONGEST survivor
+        // list of its lanes per mask, so one list per waypoint (instead of one per three obstacles) keeps the lanes'
+        // lists as even as they get.  Capsules on links that no joint moves have a zero distance gradient: an active
+        // one adds nothing to (A, b), so they are not tested at all.
+        constexpr int OGRP = 64 / M::NCAP;
         for (int o0 = 0; o0 < tb.ob.n; o0 += OGRP) {
-            unsigned mask = 0u;
-#pragma unroll 1  // one copy of the 9 x 15-instruction cull block (and of its rotated-cuboid variant) in the kernel
+            unsigned long long mask = 0ull;
+#pragma unroll 1  // one copy of the 9 x 12-instruction cull block (and of its rotated-cuboid variant) in the kernel
             for (int oo = 0; oo < OGRP; ++oo)
-                if (o0 + oo < tb.ob.n) mask |= env_cull_mask<M, n_static_capsules<M>()>(sink.mid2, tb.ob, o0 + oo) << (oo * M::NCAP);
+                if (o0 + oo < tb.ob.n)
+                    mask |= (unsigned long long)env_cull_mask<M, n_static_capsules<M>()>(sink.mid2, tb.ob, o0 + oo) << (oo * M::NCAP);
             while (mask) {
-                const int bit = __ffs(mask) - 1;
+                const int bit = __ffsll((long long)mask) - 1;
                 mask &= mask - 1;
                 const int oo = bit / M::NCAP, c = bit - oo * M::NCAP;
                 float Cw[3], nrm[3];
@@ -971,6 +973,7 @@ lm_block_solve_v2_kernel(const float* __restrict__ q, int64_t P, int64_t T, cons
     }
 }
 
+constexpr int64_t SOLVE_V2_MAX_PATHS_ALONE = 1024, SOLVE_V2_MAX_PATHS_OVERLAP = 256;  // see launch_solve
 constexpr int64_t SOLVE_RESIDENT_MAX_PATHS = 8;  // beyond a handful of paths the streaming kernel's throughput wins
 
 template <class M>
@@ -1099,7 +1102,13 @@ static int launch_solve(const cppflow_lm_params* p, const float* q, int64_t P, i
         return launch_solve_variant<M, 3, 8>(sp, q, P, T, (flags & CPPFLOW_LM_OVERLAP) != 0, ws, x_out, st);
     if (which && std::strcmp(which, "tma1") == 0)
         return launch_solve_variant<M, 4, 1>(sp, q, P, T, (flags & CPPFLOW_LM_OVERLAP) != 0, ws, x_out, st);
-    if (flags & CPPFLOW_LM_OVERLAP) return launch_solve_variant<M, SOLVE_RING_OVERLAP>(sp, q, P, T, true, ws, x_out, st);
+    // few paths: the chain latency is all there is, and the register-resident kernel's step is the shortest (no ring
+    // bookkeeping): P = 512 alone 0.128 ms against 0.21; under overlap it only wins for chunks of <= 256 paths
+    // (4 chunks of 256: 0.203 ms per iteration against 0.254, of 512: 0.337 against 0.286).  Bit-identical either way.
+    const bool overlap = (flags & CPPFLOW_LM_OVERLAP) != 0;
+    if (!which && P <= (overlap ? SOLVE_V2_MAX_PATHS_OVERLAP : SOLVE_V2_MAX_PATHS_ALONE))
+        return launch_solve_v2<M, 1, true>(sp, q, P, T, overlap, ws, x_out, st);
+    if (overlap) return launch_solve_variant<M, SOLVE_RING_OVERLAP>(sp, q, P, T, true, ws, x_out, st);
     return launch_solve_variant<M, SOLVE_RING_ALONE>(sp, q, P, T, false, ws, x_out, st);
 }
 
