@@ -436,21 +436,36 @@ def main():
     # ---- e2e: host buffers in, host buffers out, through the public API, copies inside the timed region
     pipe = HostPipeline(problem, P, all_terms_parameters())
     with numa_local(dev):
-        out_host = torch.empty_like(x_host).pin_memory()
+        out_hosts = [torch.empty_like(x_host).pin_memory() for _ in range(pipe.depth)]
+    out_host = out_hosts[0]
     e2e_steps = max(3, min(steps, 20))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for _ in range(2):
-        pipe.refine(x_host, out_host)
+    for i in range(2 * pipe.depth):
+        pipe.refine_async(x_host, out_hosts[i % pipe.depth])
     barrier()
+    # every step is an independent job (host paths in, refined host paths out) submitted with refine_async: a step's
+    # copy-in runs under the copy-out of the step before it (two slots of device buffers); the region ends when the
+    # last step's result is in host memory
     t0 = time.perf_counter()
     e0.record()
-    for _ in range(e2e_steps):
-        pipe.refine(x_host, out_host)
+    done = [pipe.refine_async(x_host, out_hosts[i % pipe.depth]) for i in range(e2e_steps)]
+    for ev in done:
+        torch.cuda.current_stream(dev).wait_event(ev)
     e1.record()
     barrier()
     wall = time.perf_counter() - t0
     e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
     e2e_value = world * evals_per_step / (e2e_ms / e2e_steps * 1e-3)
+    # the same job one call at a time (each refine joins the caller's stream before the next starts): its latency
+    for _ in range(2):
+        pipe.refine(x_host, out_host)
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        pipe.refine(x_host, out_host)
+    e1.record()
+    barrier()
+    e2e_serial_ms = max_over_ranks(e0.elapsed_time(e1)) / e2e_steps
     h2d = x_host.numel() * 4
     d2h = out_host.numel() * 4
 
@@ -690,7 +705,9 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "waypoint-evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": wall / e2e_steps * 1e3, "steps": e2e_steps,
-                "api": "cppflow_b200.pipeline.HostPipeline.refine(host x -> host x_new), pinned host buffers"},
+                "api": "cppflow_b200.pipeline.HostPipeline.refine_async(host x -> host x_new), pinned host buffers, "
+                       "independent steps two deep in flight",
+                "ms_per_step_one_at_a_time": e2e_serial_ms},
         "gpu_launches": steps * 2 * len(rpipe.chunks) + len(rpipe.chunks),
         "ms_per_step_without_tail": ms_steps_only,
         "single_stream_ms_per_step": ms_single,

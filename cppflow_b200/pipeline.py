@@ -6,12 +6,17 @@ max(copy in, compute, copy out) instead of their sum.  The kernels of consecutiv
 (round robin over `n_run_streams`): the block solve of a chunk is a latency-bound chain of T dependent steps that
 fills only a few SMs, so it overlaps the assembly and the solves of its neighbours.
 
-The whole fork / copy / launch / join pattern of one `refine` call (4 operations per chunk on 2 + n_run_streams
-streams) is captured once per (input buffer, output buffer) pair into a CUDA graph and replayed (enqueueing it from
-Python costs ~60 us per chunk).  Measured at P = 8192, T = 300 (78.6 MB each way, 55 GB/s per direction alone =
-1.42 ms): 16 chunks / 4 run streams 2.11 ms per step; 32 / 8: 2.35; 64 / 16: 2.84 - smaller chunks do not shorten the
-exposed tail, which is the ~0.3 ms latency of one chunk's block solve whatever its size, and chunks below 256 paths
-leave lanes of the 256-thread assembly CTAs idle."""
+The whole fork / copy / launch / join pattern of one call (4 operations per chunk on 2 + n_run_streams streams) is
+captured once per (slot, input buffer, output buffer) into a CUDA graph and replayed (enqueueing it from Python costs
+~60 us per chunk).  Independent jobs submitted with `refine_async` go to `depth` slots of device buffers in turn and
+overlap: the copy-in of one job runs under the copy-out of the job before it.
+
+Measured at P = 8192, T = 300 (78.6 MB each way; one direction alone 1.42 ms, both directions at once 1.64 ms = the
+floor): one job at a time 2.23-2.24 ms per job whatever the chunking (first copy-in, last solve and last copy-out are
+exposed); two jobs deep: 16 chunks 2.00 ms, 8 chunks 1.94, 6 chunks / 3 run streams **1.75** (0.93 of the floor), 4
+chunks 1.86, 3 chunks 1.88; a third slot changes nothing (1.76).  Every event between a copy and a kernel costs the
+copy engines time (48.8 -> ~36 GB/s per direction with 16 chunks), so with the fill and drain hidden by the next job
+fewer, larger chunks win until a chunk's own latency shows again."""
 from typing import Optional
 
 import torch
@@ -68,8 +73,8 @@ class numa_local:
 
 class HostPipeline:
     def __init__(self, problem: Problem, n_paths: int, params: Optional[OptimizationParameters] = None,
-                 n_chunks: int = 16, n_run_streams: int = 4, device=None, use_graph: bool = True, overlap: bool = True,
-                 taper=None):
+                 n_chunks: int = 6, n_run_streams: int = 3, device=None, use_graph: bool = True, overlap: bool = True,
+                 taper=None, depth: int = 2):
         """`taper`: path counts of extra small chunks at BOTH ends of the chunk list, e.g. (64, 192): the first result
         can only leave for the host one chunk latency (copy-in + assembly + the solve's ~0.25 ms chain) after the
         start, and the last chunk's latency is exposed after the last copy-in - small first and last chunks shorten both."""
@@ -93,41 +98,69 @@ class HostPipeline:
             start += n
         assert start == n_paths
         D = self.robot.ndof
-        self.x_dev = torch.empty((n_paths * self.T, D), device=self.device, dtype=torch.float32)
-        self.out_dev = torch.empty_like(self.x_dev)
+        # `depth` independent slots (device buffers, workspaces, events, launch stream): consecutive refine_async calls
+        # alternate between them, so the copy-in of one call runs under the copy-out of the call before it
+        self.depth = max(1, int(depth))
+        self.x_devs = [torch.empty((n_paths * self.T, D), device=self.device, dtype=torch.float32) for _ in range(self.depth)]
+        self.out_devs = [torch.empty_like(self.x_devs[0]) for _ in range(self.depth)]
+        self.x_dev, self.out_dev = self.x_devs[0], self.out_devs[0]
         self.s_in, self.s_out = (torch.cuda.Stream(self.device) for _ in range(2))
         self.s_run = [torch.cuda.Stream(self.device) for _ in range(max(1, min(n_run_streams, n_chunks)))]
-        self.ev_in = [torch.cuda.Event() for _ in self.chunks]
-        self.ev_run = [torch.cuda.Event() for _ in self.chunks]
-        # one workspace per run stream (kernels on one stream are ordered, so its workspace is reused safely)
+        self.s_launch = [torch.cuda.Stream(self.device) for _ in range(self.depth)]
+        self.ev_in = [[torch.cuda.Event() for _ in self.chunks] for _ in range(self.depth)]
+        self.ev_run = [[torch.cuda.Event() for _ in self.chunks] for _ in range(self.depth)]
+        # one workspace per (slot, run stream) (kernels on one stream are ordered, so its workspace is reused safely)
         lib_bytes = ops._lib.load().cppflow_lm_full_workspace_bytes(self.robot.robot_id, max(n for _, n in self.chunks), self.T)
-        self.ws = [torch.empty((lib_bytes,), device=self.device, dtype=torch.uint8) for _ in self.s_run]
+        self.wss = [[torch.empty((lib_bytes,), device=self.device, dtype=torch.uint8) for _ in self.s_run]
+                    for _ in range(self.depth)]
         self.use_graph = use_graph
         self.flags = ops.LM_CLAMP | (ops.LM_OVERLAP if overlap else 0)  # overlap: the solve of a chunk runs under the
         self._graphs = {}                                              # assembly of the next (see ResidentPipeline)
+        self._next = 0
 
     def refine(self, x_host: torch.Tensor, out_host: torch.Tensor) -> torch.Tensor:
         """One fused LM iteration (+ clamp) over all paths: x_host [P*T, D] pinned -> out_host [P*T, D] pinned.
         Asynchronous with respect to the host: the caller's current stream waits for the last copy."""
-        assert x_host.shape == self.x_dev.shape and out_host.shape == self.x_dev.shape
-        assert x_host.is_pinned() and out_host.is_pinned(), "host buffers must be pinned for asynchronous copies"
-        if not self.use_graph:
-            return self._enqueue(x_host, out_host)
-        key = (x_host.data_ptr(), out_host.data_ptr())
-        graph = self._graphs.get(key)
-        if graph is None:
-            self._enqueue(x_host, out_host)  # eager once: first-call setup inside the library must not be captured
-            torch.cuda.current_stream(self.device).synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                self._enqueue(x_host, out_host)
-            self._graphs[key] = graph
-        graph.replay()
+        done = self.refine_async(x_host, out_host)
+        torch.cuda.current_stream(self.device).wait_event(done)
         return out_host
 
-    def _enqueue(self, x_host: torch.Tensor, out_host: torch.Tensor) -> torch.Tensor:
+    def refine_async(self, x_host: torch.Tensor, out_host: torch.Tensor) -> torch.cuda.Event:
+        """The same iteration, submitted without joining the caller's stream: returns the event that completes when
+        out_host is filled (`event.synchronize()` before reading it on the CPU).  Calls go to `depth` slots in turn, each
+        ordered after the caller's current stream at submission; calls in different slots overlap on the device (PCIe
+        is full duplex: the copy-in of call i + 1 runs under the copy-out of call i), so a stream of independent
+        path sets is refined at max(copy in, copy out) per set instead of their pipelined sum.  The caller keeps
+        x_host unchanged and out_host unread until the event completes, and passes distinct out_host buffers to calls
+        that may be in flight together."""
+        assert x_host.shape == self.x_dev.shape and out_host.shape == self.x_dev.shape
+        assert x_host.is_pinned() and out_host.is_pinned(), "host buffers must be pinned for asynchronous copies"
+        slot = self._next
+        self._next = (self._next + 1) % self.depth
+        launch = self.s_launch[slot]
+        launch.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(launch):
+            if not self.use_graph:
+                self._enqueue(x_host, out_host, slot)
+            else:
+                key = (slot, x_host.data_ptr(), out_host.data_ptr())
+                graph = self._graphs.get(key)
+                if graph is None:
+                    self._enqueue(x_host, out_host, slot)  # eager once: first-call setup in the library must not be captured
+                    launch.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        self._enqueue(x_host, out_host, slot)
+                    self._graphs[key] = graph
+                graph.replay()
+            done = torch.cuda.Event()
+            done.record(launch)
+        return done
+
+    def _enqueue(self, x_host: torch.Tensor, out_host: torch.Tensor, slot: int = 0) -> torch.Tensor:
         T, D, rid = self.T, self.robot.ndof, self.robot.robot_id
         cur = torch.cuda.current_stream(self.device)
+        x_dev, out_dev = self.x_devs[slot], self.out_devs[slot]
         for s in [self.s_in, self.s_out] + self.s_run:
             s.wait_stream(cur)
         lib = ops._lib.load()
@@ -135,19 +168,19 @@ class HostPipeline:
         for c, (p0, n) in enumerate(self.chunks):
             sl = slice(p0 * T, (p0 + n) * T)
             with torch.cuda.stream(self.s_in):
-                self.x_dev[sl].copy_(x_host[sl], non_blocking=True)
-                self.ev_in[c].record(self.s_in)
+                x_dev[sl].copy_(x_host[sl], non_blocking=True)
+                self.ev_in[slot][c].record(self.s_in)
             s_run = self.s_run[c % len(self.s_run)]
             with torch.cuda.stream(s_run):
-                s_run.wait_event(self.ev_in[c])
-                ws = self.ws[c % len(self.s_run)]
+                s_run.wait_event(self.ev_in[slot][c])
+                ws = self.wss[slot][c % len(self.s_run)]
                 ops.check(lib.cppflow_lm_full_step(
-                    rid, self.prm, ops.ptr(self.x_dev[sl]), None, ops.ptr(self.problem.target_path), n, T, cu, tc, no, self.flags,
-                    ops.ptr(ws), ws.numel(), ops.ptr(self.out_dev[sl]), ops.stream_ptr(self.device)))
-                self.ev_run[c].record(s_run)
+                    rid, self.prm, ops.ptr(x_dev[sl]), None, ops.ptr(self.problem.target_path), n, T, cu, tc, no, self.flags,
+                    ops.ptr(ws), ws.numel(), ops.ptr(out_dev[sl]), ops.stream_ptr(self.device)))
+                self.ev_run[slot][c].record(s_run)
             with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(self.ev_run[c])
-                out_host[sl].copy_(self.out_dev[sl], non_blocking=True)
+                self.s_out.wait_event(self.ev_run[slot][c])
+                out_host[sl].copy_(out_dev[sl], non_blocking=True)
         for s in [self.s_out, self.s_in] + self.s_run:
             cur.wait_stream(s)
         return out_host

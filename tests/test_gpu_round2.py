@@ -404,3 +404,36 @@ def test_plan_from_qpath(name):
         assert bool(plan.env_colliding_per_ts.any()) == (float(ref["min_env"]) < 0)
         assert plan.is_valid == rep.is_valid
         assert isinstance(PlanNp(plan).q_path, np.ndarray)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# host-buffer pipeline: jobs in flight together give the results of the jobs run one at a time
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_host_pipeline_async_jobs_match_single_step(robots, use_graph):
+    from cppflow_b200 import ops
+    from cppflow_b200.lm_hyper_parameters import all_terms_parameters
+    from cppflow_b200.pipeline import HostPipeline
+    from cppflow_b200.synthetic import synthetic_problem as device_problem, synthetic_seeds_host
+
+    robot, P, T = robots["fetch"], 600, 61  # ragged: 600 paths over 7 chunks
+    problem = device_problem(robot, T, seed=0, device=DEV)
+    jobs = [synthetic_seeds_host(robot, P, T, seed=0, shard=k, pin=True)[1] for k in range(5)]
+    outs = [torch.empty_like(j).pin_memory() for j in jobs]
+    pipe = HostPipeline(problem, P, all_terms_parameters(), n_chunks=7, n_run_streams=3, use_graph=use_graph)
+    prm = ops.make_params(all_terms_parameters())
+    for rep in range(2):  # second round: graphs replayed, slots reused
+        for o in outs:
+            o.fill_(float("nan"))
+        done = [pipe.refine_async(j, o) for j, o in zip(jobs, outs)]
+        for ev in done:
+            ev.synchronize()
+        for j, o in zip(jobs, outs):
+            ref = ops.lm_full_step(robot.robot_id, robot.ndof, prm, j.to(DEV), None, problem.target_path, P, T,
+                                   problem.obstacle_tables, True)
+            assert torch.equal(o, ref.cpu()), "a job in flight next to another must equal the job run alone, bit for bit"
+    out2 = torch.empty_like(jobs[0]).pin_memory()
+    pipe.refine(jobs[0], out2)
+    torch.cuda.current_stream().synchronize()
+    assert torch.equal(out2, outs[0])
