@@ -60,7 +60,7 @@ inline int make_obstacles(const float* h_cuboids, const float* h_Tcuboids, int n
 
 // cppflow_path_metrics with a completion tag in column 7 of every row (k_metrics.cu)
 int path_metrics_tagged(int robot, const float* d_q, const float* d_target, int64_t P, int64_t T, const float* h_cuboids,
-                        const float* h_Tcuboids, int n_obstacles, float* d_out, float tag, void* stream);
+                        const float* h_Tcuboids, int n_obstacles, float* d_out, float tag, void* stream, int flags = 0);
 
 // pose-only LM step of one path (T <= 1024) fused with the metrics of the new path (k_metrics.cu)
 int pose_step_metrics_tagged(int robot, const cppflow_lm_params* params, const float* d_q, const float* d_target, int64_t T,

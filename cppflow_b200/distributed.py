@@ -96,7 +96,11 @@ def enqueue_argmin(metrics: torch.Tensor, constraints, first_index: int, world: 
     int64 of every rank - all enqueued on the current stream / the process group's stream, no host synchronisation."""
     assert first_index + metrics.shape[0] < (1 << _IDX_BITS), "global path index must fit 31 bits"
     dev = metrics.device
-    if metrics.shape[0] > 0:
+    if metrics.shape[0] > 0 and metrics.is_cuda:
+        from . import ops  # one launch of the library's key + argmin kernel (the torch arithmetic below: ~25 launches)
+
+        local = ops.path_key_argmin(metrics.contiguous(), constraints, first_index)
+    elif metrics.shape[0] > 0:
         keys = path_keys(metrics, constraints, first_index)
         local = torch.stack([keys.min(), (keys >> _INVALID_SHIFT == 0).sum(),
                              torch.tensor(first_index, device=dev, dtype=torch.int64)])

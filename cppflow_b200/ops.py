@@ -294,16 +294,38 @@ def dp_search(rid: int, ndof: int, q: torch.Tensor, self_flags: torch.Tensor, en
 METRIC_NAMES = ("max_pos_cm", "max_rot_deg", "mjac_deg", "mjac_cm", "tl", "min_self", "min_env")
 
 
+METRICS_SIGN_ONLY = 1  # CPPFLOW_METRICS_SIGN_ONLY
+
+
 @_on_device
 def path_metrics(rid: int, ndof: int, q: torch.Tensor, target: torch.Tensor, P: int, T: int,
-                 ob: Optional[Obstacles]) -> torch.Tensor:
+                 ob: Optional[Obstacles], sign_only: bool = False) -> torch.Tensor:
+    """[P, 8] metrics (METRIC_NAMES).  `sign_only`: the two minimum-distance columns are exact only when negative
+    (enough for x_is_valid and the cost ranking; about half the time for thousands of paths)."""
     q = _check_q(q, ndof)
     assert q.shape[0] == P * T
     target = require_cuda(target, "target_path")
     assert target.shape == (T, 7)
     out = torch.empty((P, 8), device=q.device, dtype=torch.float32)
     cu, tc, no = _obs(ob)
-    check(_lib.load().cppflow_path_metrics(rid, ptr(q), ptr(target), P, T, cu, tc, no, ptr(out), stream_ptr(q.device)))
+    check(_lib.load().cppflow_path_metrics_ex(rid, ptr(q), ptr(target), P, T, cu, tc, no, METRICS_SIGN_ONLY if sign_only else 0,
+                                              ptr(out), stream_ptr(q.device)))
+    return out
+
+
+@_on_device
+def path_key_argmin(metrics: torch.Tensor, constraints, first_index: int) -> torch.Tensor:
+    """int64 [3] = (smallest ranking key, number of valid paths, first_index) of the [P, 8] metrics rows, one launch
+    (distributed.path_keys is the same arithmetic in torch)."""
+    metrics = require_cuda(metrics, "metrics")
+    assert metrics.dtype == torch.float32 and metrics.dim() == 2 and metrics.shape[1] == 8 and metrics.is_contiguous()
+    out = torch.empty((3,), device=metrics.device, dtype=torch.int64)
+    cons = _lib.ConstraintsC(constraints.max_allowed_position_error_cm, constraints.max_allowed_rotation_error_deg,
+                             constraints.max_allowed_mjac_deg, constraints.max_allowed_mjac_cm)
+    import ctypes as C
+
+    check(_lib.load().cppflow_path_key_argmin(ptr(metrics), metrics.shape[0], C.byref(cons), first_index, ptr(out),
+                                              stream_ptr(metrics.device)))
     return out
 
 

@@ -301,17 +301,19 @@ class ResidentPipeline:
                 ops.lm_full_step(rid, D, self.prm, x[sl], None, self.problem.target_path, n, T,
                                  self.problem.obstacle_tables, clamp, out=out[sl], overlap=self.overlap, workspace=ws)
 
-    def enqueue_metrics(self, x: torch.Tensor, metrics: torch.Tensor):
+    def enqueue_metrics(self, x: torch.Tensor, metrics: torch.Tensor, sign_only: bool = True):
         """Per-path validity metrics of x ([P*T, D]) into `metrics` ([P, 8]), each chunk's rows on the chunk's own stream
         right behind its last step - the metrics of a finished chunk run under the last solves of the others.  Call
-        between begin() and end()."""
+        between begin() and end().  `sign_only` (default): what validity and the cost ranking need - the minimum capsule
+        distances are exact only when negative (ops.path_metrics)."""
         T, D, rid = self.T, self.robot.ndof, self.robot.robot_id
         lib = ops._lib.load()
         cu, tc, no = ops._obs(self.problem.obstacle_tables)
         last = self.solve_streams if self.partition is not None else self.streams  # where a chunk's last solve ran
         for (p0, n), s in zip(self.chunks, last):
-            ops.check(lib.cppflow_path_metrics(rid, ops.ptr(x[p0 * T:(p0 + n) * T]), ops.ptr(self.problem.target_path), n, T,
-                                               cu, tc, no, ops.ptr(metrics[p0:p0 + n]), s.cuda_stream))
+            ops.check(lib.cppflow_path_metrics_ex(rid, ops.ptr(x[p0 * T:(p0 + n) * T]), ops.ptr(self.problem.target_path), n, T,
+                                                  cu, tc, no, ops.METRICS_SIGN_ONLY if sign_only else 0,
+                                                  ops.ptr(metrics[p0:p0 + n]), s.cuda_stream))
 
     def iterate(self, x: torch.Tensor, n_iters: int, clamp: bool = True) -> torch.Tensor:
         """n_iters dependent LM iterations (x <- step(x)); returns the refined paths (a new tensor; x is kept)."""

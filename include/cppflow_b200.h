@@ -241,6 +241,22 @@ int cppflow_dp_search(int robot, const float* d_q, const uint8_t* d_self_flags, 
  *  trajectory length rad, min capsule self distance m, min capsule env distance m (+inf if no obstacles), 0}. */
 int cppflow_path_metrics(int robot, const float* d_q, const float* d_target, int64_t P, int64_t T,
                          const float* h_cuboids, const float* h_Tcuboids, int n_obstacles, float* d_out, void* stream);
+/* The same with options.  CPPFLOW_METRICS_SIGN_ONLY: x_is_valid (optimization_utils.py:889-900) and the cost ranking only
+ * ask whether a path collides, so only capsule pairs that bounding spheres cannot prove apart are evaluated: columns
+ * 5 / 6 are the exact minimum distance when it is negative, and otherwise some non-negative number (+inf when every pair
+ * was proven apart).  Every other column is unchanged. */
+#define CPPFLOW_METRICS_SIGN_ONLY 1
+int cppflow_path_metrics_ex(int robot, const float* d_q, const float* d_target, int64_t P, int64_t T,
+                            const float* h_cuboids, const float* h_Tcuboids, int n_obstacles, int flags, float* d_out,
+                            void* stream);
+
+/* Ranking of refined paths (north star: "gather per-path costs and the argmin"; no reference counterpart - the reference
+ * refines one path).  A path is ranked by (invalid, trajectory length, global index): key = invalid << 62 |
+ * bits(float32 TL) << 31 | (first_index + p), valid = the four thresholds of x_is_valid (evaluation_utils.py:41-58) and
+ * no negative capsule distance.  d_metrics [P,8] = rows of cppflow_path_metrics; d_out int64[3] = {smallest key, number of
+ * valid paths, first_index} - what each rank contributes to the all-gather. */
+int cppflow_path_key_argmin(const float* d_metrics, int64_t P, const cppflow_constraints* constraints,
+                            int64_t first_index, int64_t* d_out, void* stream);
 
 /* Splits the SMs of `device` into two green contexts - the first with at least `min_sms_first` SMs (rounded up to the
  * architecture's granularity, 8 on sm_90+), the second with the rest - and creates streams in each.  Kernels launched

@@ -210,6 +210,15 @@ def test_path_metrics_all_columns(robots, r, T):
         n_valid += bool(valid)
         n_coll += bool(ref["min_self"] < 0 or ref["min_env"] < 0)
     assert n_coll >= len(check) // 6, n_coll
+    # sign-only variant (validity / cost ranking): every other column bit-identical, the two minima exact where negative
+    # and non-negative where the exact minimum is
+    sign = ops.path_metrics(rob.robot_id, rob.ndof, xd, td, P, T, ob, sign_only=True).cpu()
+    assert torch.equal(sign[:, :5], many[:, :5])
+    for k in (5, 6):
+        neg = many[:, k] < 0
+        assert torch.equal(sign[neg, k], many[neg, k])
+        assert bool((sign[~neg, k] >= 0).all())
+    assert int((many[:, 5:7] < 0).any(dim=1).sum()) >= P // 6
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -437,3 +446,39 @@ def test_host_pipeline_async_jobs_match_single_step(robots, use_graph):
     pipe.refine(jobs[0], out2)
     torch.cuda.current_stream().synchronize()
     assert torch.equal(out2, outs[0])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# ranking key + local argmin: the library's one-launch kernel against the torch arithmetic of distributed.path_keys
+
+
+@pytest.mark.parametrize("P", [1, 37, 8192, 70001])
+@pytest.mark.parametrize("all_invalid", [False, True])
+def test_native_key_argmin_matches_torch_keys(P, all_invalid):
+    from cppflow_b200 import ops
+    from cppflow_b200.data_types import DEFAULT_CONSTRAINTS as C
+    from cppflow_b200.distributed import path_keys, enqueue_argmin, _INVALID_SHIFT
+
+    g = torch.Generator().manual_seed(P)
+    m = torch.zeros((P, 8))
+    m[:, 0] = torch.rand(P, generator=g) * 2 * C.max_allowed_position_error_cm  # half of the paths break a threshold
+    m[:, 1] = torch.rand(P, generator=g) * 1.2 * C.max_allowed_rotation_error_deg
+    m[:, 2] = torch.rand(P, generator=g) * 1.1 * C.max_allowed_mjac_deg
+    m[:, 3] = torch.rand(P, generator=g) * 1.1 * C.max_allowed_mjac_cm
+    m[:, 4] = torch.rand(P, generator=g) * 50 + 1
+    m[:, 5] = torch.rand(P, generator=g) - 0.1
+    m[:, 6] = torch.where(torch.rand(P, generator=g) < 0.3, torch.full((P,), float("inf")), torch.rand(P, generator=g) - 0.1)
+    if all_invalid:
+        m[:, 0] = 1.0
+    if P > 30:
+        m[3, 4] = m[29, 4] = 0.5                       # a tie: the lowest index wins
+        m[7, 4] = float("nan")                         # NaN trajectory length: invalid, sorts last
+        m[11, 0] = C.max_allowed_position_error_cm     # equality with a threshold is not below it (float32 comparison)
+        m[13, 5] = 0.0                                 # a distance of exactly zero is not a collision
+    first = 1000
+    md = m.to(DEV)
+    keys = path_keys(md, C, first)
+    want = [int(keys.min()), int((keys >> _INVALID_SHIFT == 0).sum()), first]
+    got = ops.path_key_argmin(md, C, first).cpu().tolist()
+    assert got == want
+    assert tuple(enqueue_argmin(md, C, first, 1).result()) == tuple(enqueue_argmin(m, C, first, 1).result())
