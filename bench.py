@@ -124,7 +124,7 @@ def cpu_reference_step_rate(T: int, sample_paths: int, steps: int, warmup: int):
     """evals/s of the reference's CPU path (oracle/ port; the reference itself needs jrl and cannot be imported):
     per path, dense LmResidualFns.get_r_and_J with every term on + _lm_full_step (dense (T*D)^2 Cholesky) + clamp."""
     from oracle import robots as OR, lm as OL
-    from tests.helpers import synthetic_problem as oracle_problem, cuboid_tensors, FETCH_CIRCLE_OBSTACLES
+    from oracle.workloads import synthetic_problem as oracle_problem, cuboid_tensors, FETCH_CIRCLE_OBSTACLES
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)

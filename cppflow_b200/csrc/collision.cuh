@@ -121,22 +121,17 @@ __device__ __forceinline__ void load_capsule(const float* sm, int c, float (&P)[
     }
 }
 
-// Signed distance of self-collision pair p; C2 = closest point on the axis of capsule b, nrm = unit vector from it
-// to the closest point on capsule a.  Pairs whose bounding spheres prove distance > cull_thr are skipped and
-// +INFINITY is returned (pass cull_thr = INFINITY to always get the exact distance).
-template <class M, int BLOCK>
-__device__ __forceinline__ float self_pair_distance(const float* sm, int p, float (&C2)[3], float (&nrm)[3],
-                                                    float cull_thr = INFINITY) {
+// ---- shared cores: the arithmetic of one capsule pair / capsule-cuboid test with its table entries passed in, so that
+// the API kernels (compile-time tables in constant memory) and the active-set kernels (tables in shared memory, runtime
+// index per lane) run the same code.
+
+// signed distance of capsules a and b; C2 = closest point on the axis of b, nrm = unit vector from it to the closest
+// point on the axis of a
+template <int BLOCK>
+__device__ __forceinline__ float capsule_pair_core(const float* sm, int a, int b, float rsum, float (&C2)[3], float (&nrm)[3]) {
     float P1[3], Q1[3], P2[3], Q2[3];
-    load_capsule<BLOCK>(sm, c_pair_table<M>.a[p], P1, Q1);
-    load_capsule<BLOCK>(sm, c_pair_table<M>.b[p], P2, Q2);
-    {
-        const float mx = (P1[0] + Q1[0]) - (P2[0] + Q2[0]);
-        const float my = (P1[1] + Q1[1]) - (P2[1] + Q2[1]);
-        const float mz = (P1[2] + Q1[2]) - (P2[2] + Q2[2]);
-        const float lim = cull_thr + c_pair_table<M>.reach[p];  // > 0 whenever a cull is intended
-        if (0.25f * (mx * mx + my * my + mz * mz) > lim * lim && lim > 0.f) return INFINITY;
-    }
+    load_capsule<BLOCK>(sm, a, P1, Q1);
+    load_capsule<BLOCK>(sm, b, P2, Q2);
     float s, t;
     segseg_closest(P1, Q1, P2, Q2, s, t);
     float diff[3];
@@ -151,14 +146,13 @@ __device__ __forceinline__ float self_pair_distance(const float* sm, int p, floa
     const float inv = d2 > 1e-24f ? rsqrtf(d2) : 0.f;
 #pragma unroll
     for (int r = 0; r < 3; ++r) nrm[r] = diff[r] * inv;
-    return dist - c_pair_table<M>.rsum[p];
+    return dist - rsum;
 }
 
-// d(distance)/dq for pair p: only the joints between the two links contribute: g_d = -n . v_d(C2)
+// d(distance)/dq of a capsule pair: only the joints between the two links (frames fa < fb) contribute: g_d = -n . v_d(C2)
 template <class M, int BLOCK>
-__device__ __forceinline__ void self_pair_gradient(const float* sm, int p, const float (&C2)[3], const float (&nrm)[3],
-                                                   float (&g)[M::NDOF]) {
-    const int fa = c_pair_table<M>.fa[p], fb = c_pair_table<M>.fb[p];
+__device__ __forceinline__ void capsule_pair_gradient_core(const float* sm, int fa, int fb, const float (&C2)[3],
+                                                           const float (&nrm)[3], float (&g)[M::NDOF]) {
     static_for<M::NDOF>([&](auto Dd) {
         constexpr int d = decltype(Dd)::value;
         constexpr int ci = chain_of_dof<M>(d);
@@ -183,26 +177,12 @@ __device__ __forceinline__ void self_pair_gradient(const float* sm, int p, const
     });
 }
 
-// signed distance of capsule c to obstacle o; Cw = closest point on the capsule axis (world), nrm = world normal
-template <class M, int BLOCK>
-__device__ __forceinline__ float env_capsule_distance(const float* sm, int c, const Obstacles& ob, int o,
-                                                      float (&Cw)[3], float (&nrm)[3], float cull_thr = INFINITY) {
-    float P[3], Q[3], A[3], B[3];
-    load_capsule<BLOCK>(sm, c, P, Q);
-    to_box_frame(ob, o, P, A);
-    to_box_frame(ob, o, Q, B);
-    {
-        // distance(segment midpoint, box) - half length - radius is a lower bound of the capsule-box distance
-        float dd = 0.f;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const float m = 0.5f * (A[r] + B[r]);
-            const float e = m - fminf(fmaxf(m, ob.lo[o][r]), ob.hi[o][r]);
-            dd = fmaf(e, e, dd);
-        }
-        const float lim = cull_thr + c_cap_table<M>.reach[c];
-        if (dd > lim * lim && lim > 0.f) return INFINITY;
-    }
+// signed distance of capsule c to obstacle o, endpoints A / B already in the cuboid's frame; Cw = closest point on the
+// capsule axis (world), nrm = world normal
+template <int BLOCK>
+__device__ __forceinline__ float capsule_cuboid_core(const float (&P)[3], const float (&Q)[3], const float (&A)[3],
+                                                     const float (&B)[3], const Obstacles& ob, int o, float radius,
+                                                     float (&Cw)[3], float (&nrm)[3]) {
     const float t = segbox_closest(A, B, ob.lo[o], ob.hi[o]);
     float diff[3];
 #pragma unroll
@@ -214,7 +194,7 @@ __device__ __forceinline__ float env_capsule_distance(const float* sm, int c, co
     const float d2 = dot3(diff, diff);
     const float dist = sqrtf(d2);
     const float inv = d2 > CPPFLOW_AXIS_INSIDE_D2 ? rsqrtf(d2) : 0.f;
-    float nb[3] = {diff[0] * inv, diff[1] * inv, diff[2] * inv};
+    const float nb[3] = {diff[0] * inv, diff[1] * inv, diff[2] * inv};
     if (ob.has_rot[o]) {
 #pragma unroll
         for (int r = 0; r < 3; ++r)
@@ -222,14 +202,13 @@ __device__ __forceinline__ float env_capsule_distance(const float* sm, int c, co
     } else {
         nrm[0] = nb[0]; nrm[1] = nb[1]; nrm[2] = nb[2];
     }
-    return dist - c_cap_table<M>.radius[c];
+    return dist - radius;
 }
 
-// d(distance)/dq for capsule c against an obstacle: g_d = n . v_d(Cw) for the joints that move the link
+// d(distance)/dq of a capsule on link frame fc against a world-fixed obstacle: g_d = n . v_d(Cw) for the joints before fc
 template <class M, int BLOCK>
-__device__ __forceinline__ void env_capsule_gradient(const float* sm, int c, const float (&Cw)[3],
-                                                     const float (&nrm)[3], float (&g)[M::NDOF]) {
-    const int fc = c_cap_table<M>.frame[c];
+__device__ __forceinline__ void capsule_cuboid_gradient_core(const float* sm, int fc, const float (&Cw)[3],
+                                                             const float (&nrm)[3], float (&g)[M::NDOF]) {
     static_for<M::NDOF>([&](auto Dd) {
         constexpr int d = decltype(Dd)::value;
         constexpr int ci = chain_of_dof<M>(d);
@@ -252,6 +231,57 @@ __device__ __forceinline__ void env_capsule_gradient(const float* sm, int c, con
         }
         g[d] = gd;
     });
+}
+
+// ---- API kernels (k_collision.cu distance / Jacobian entry points, single-path metrics): compile-time tables.
+// Pairs whose bounding spheres prove distance > cull_thr are skipped and +INFINITY is returned (cull_thr = INFINITY:
+// always the exact distance).
+template <class M, int BLOCK>
+__device__ __forceinline__ float self_pair_distance(const float* sm, int p, float (&C2)[3], float (&nrm)[3],
+                                                    float cull_thr = INFINITY) {
+    const int a = c_pair_table<M>.a[p], b = c_pair_table<M>.b[p];
+    {
+        float P1[3], Q1[3], P2[3], Q2[3];
+        load_capsule<BLOCK>(sm, a, P1, Q1);
+        load_capsule<BLOCK>(sm, b, P2, Q2);
+        const float mx = (P1[0] + Q1[0]) - (P2[0] + Q2[0]);
+        const float my = (P1[1] + Q1[1]) - (P2[1] + Q2[1]);
+        const float mz = (P1[2] + Q1[2]) - (P2[2] + Q2[2]);
+        const float lim = cull_thr + c_pair_table<M>.reach[p];  // > 0 whenever a cull is intended
+        if (0.25f * (mx * mx + my * my + mz * mz) > lim * lim && lim > 0.f) return INFINITY;
+    }
+    return capsule_pair_core<BLOCK>(sm, a, b, c_pair_table<M>.rsum[p], C2, nrm);
+}
+template <class M, int BLOCK>
+__device__ __forceinline__ void self_pair_gradient(const float* sm, int p, const float (&C2)[3], const float (&nrm)[3],
+                                                   float (&g)[M::NDOF]) {
+    capsule_pair_gradient_core<M, BLOCK>(sm, c_pair_table<M>.fa[p], c_pair_table<M>.fb[p], C2, nrm, g);
+}
+template <class M, int BLOCK>
+__device__ __forceinline__ float env_capsule_distance(const float* sm, int c, const Obstacles& ob, int o,
+                                                      float (&Cw)[3], float (&nrm)[3], float cull_thr = INFINITY) {
+    float P[3], Q[3], A[3], B[3];
+    load_capsule<BLOCK>(sm, c, P, Q);
+    to_box_frame(ob, o, P, A);
+    to_box_frame(ob, o, Q, B);
+    {
+        // distance(segment midpoint, box) - half length - radius is a lower bound of the capsule-box distance
+        float dd = 0.f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float m = 0.5f * (A[r] + B[r]);
+            const float e = m - fminf(fmaxf(m, ob.lo[o][r]), ob.hi[o][r]);
+            dd = fmaf(e, e, dd);
+        }
+        const float lim = cull_thr + c_cap_table<M>.reach[c];
+        if (dd > lim * lim && lim > 0.f) return INFINITY;
+    }
+    return capsule_cuboid_core<BLOCK>(P, Q, A, B, ob, o, c_cap_table<M>.radius[c], Cw, nrm);
+}
+template <class M, int BLOCK>
+__device__ __forceinline__ void env_capsule_gradient(const float* sm, int c, const float (&Cw)[3],
+                                                     const float (&nrm)[3], float (&g)[M::NDOF]) {
+    capsule_cuboid_gradient_core<M, BLOCK>(sm, c_cap_table<M>.frame[c], Cw, nrm, g);
 }
 
 
@@ -419,117 +449,33 @@ __device__ __forceinline__ unsigned env_cull_mask(const float (&mid2)[M::NCAP][3
     return mask;
 }
 
-// exact signed distance of pair p (runtime index; tables from shared memory); C2 / nrm as in self_pair_distance
+// ---- active-set kernels: runtime pair / capsule index per lane, tables from shared memory
 template <class M, int BLOCK>
 __device__ __forceinline__ float self_pair_exact(const float* sm, const CollTables<M>& tb, int p, float (&C2)[3],
                                                  float (&nrm)[3]) {
     const int ab = tb.pair_ab[p];
-    float P1[3], Q1[3], P2[3], Q2[3];
-    load_capsule<BLOCK>(sm, ab & 0xff, P1, Q1);
-    load_capsule<BLOCK>(sm, (ab >> 8) & 0xff, P2, Q2);
-    float s, t;
-    segseg_closest(P1, Q1, P2, Q2, s, t);
-    float diff[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const float c1 = fmaf(s, Q1[r] - P1[r], P1[r]);
-        C2[r] = fmaf(t, Q2[r] - P2[r], P2[r]);
-        diff[r] = c1 - C2[r];
-    }
-    const float d2 = dot3(diff, diff);
-    const float dist = sqrtf(d2);
-    const float inv = d2 > 1e-24f ? rsqrtf(d2) : 0.f;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) nrm[r] = diff[r] * inv;
-    return dist - tb.pair_rsum[p];
+    return capsule_pair_core<BLOCK>(sm, ab & 0xff, (ab >> 8) & 0xff, tb.pair_rsum[p], C2, nrm);
 }
-
 template <class M, int BLOCK>
 __device__ __forceinline__ void self_pair_gradient_rt(const float* sm, const CollTables<M>& tb, int p,
                                                       const float (&C2)[3], const float (&nrm)[3], float (&g)[M::NDOF]) {
     const int ab = tb.pair_ab[p];
-    const int fa = (ab >> 16) & 0xff, fb = (ab >> 24) & 0xff;
-    static_for<M::NDOF>([&](auto Dd) {
-        constexpr int d = decltype(Dd)::value;
-        constexpr int ci = chain_of_dof<M>(d);
-        float gd = 0.f;
-        if (ci >= fa && ci < fb) {
-            float a[3], o[3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                a[r] = sm[(SmemLayout<M>::JOINTS + d * 6 + r) * BLOCK];
-                o[r] = sm[(SmemLayout<M>::JOINTS + d * 6 + 3 + r) * BLOCK];
-            }
-            if constexpr (dof_is_prismatic<M>(d)) {
-                gd = -dot3(nrm, a);
-            } else {
-                const float rr[3] = {C2[0] - o[0], C2[1] - o[1], C2[2] - o[2]};
-                float v[3];
-                cross3(a, rr, v);
-                gd = -dot3(nrm, v);
-            }
-        }
-        g[d] = gd;
-    });
+    capsule_pair_gradient_core<M, BLOCK>(sm, (ab >> 16) & 0xff, (ab >> 24) & 0xff, C2, nrm, g);
 }
-
 template <class M, int BLOCK>
 __device__ __forceinline__ float env_capsule_exact(const float* sm, const CollTables<M>& tb, int c, int o,
                                                    float (&Cw)[3], float (&nrm)[3]) {
-    const Obstacles& ob = tb.ob;
     float P[3], Q[3], A[3], B[3];
     load_capsule<BLOCK>(sm, c, P, Q);
-    to_box_frame(ob, o, P, A);
-    to_box_frame(ob, o, Q, B);
-    const float t = segbox_closest(A, B, ob.lo[o], ob.hi[o]);
-    float diff[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const float cb = fmaf(t, B[r] - A[r], A[r]);
-        diff[r] = cb - fminf(fmaxf(cb, ob.lo[o][r]), ob.hi[o][r]);
-        Cw[r] = fmaf(t, Q[r] - P[r], P[r]);
-    }
-    const float d2 = dot3(diff, diff);
-    const float dist = sqrtf(d2);
-    const float inv = d2 > CPPFLOW_AXIS_INSIDE_D2 ? rsqrtf(d2) : 0.f;
-    const float nb[3] = {diff[0] * inv, diff[1] * inv, diff[2] * inv};
-    if (ob.has_rot[o]) {
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-            nrm[r] = fmaf(ob.R[o][3 * r + 2], nb[2], fmaf(ob.R[o][3 * r + 1], nb[1], ob.R[o][3 * r] * nb[0]));
-    } else {
-        nrm[0] = nb[0]; nrm[1] = nb[1]; nrm[2] = nb[2];
-    }
-    return dist - tb.cap_radius[c];
+    to_box_frame(tb.ob, o, P, A);
+    to_box_frame(tb.ob, o, Q, B);
+    return capsule_cuboid_core<BLOCK>(P, Q, A, B, tb.ob, o, tb.cap_radius[c], Cw, nrm);
 }
-
 template <class M, int BLOCK>
 __device__ __forceinline__ void env_capsule_gradient_rt(const float* sm, const CollTables<M>& tb, int c,
                                                         const float (&Cw)[3], const float (&nrm)[3],
                                                         float (&g)[M::NDOF]) {
-    const int fc = tb.cap_frame[c];
-    static_for<M::NDOF>([&](auto Dd) {
-        constexpr int d = decltype(Dd)::value;
-        constexpr int ci = chain_of_dof<M>(d);
-        float gd = 0.f;
-        if (ci < fc) {
-            float a[3], o[3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                a[r] = sm[(SmemLayout<M>::JOINTS + d * 6 + r) * BLOCK];
-                o[r] = sm[(SmemLayout<M>::JOINTS + d * 6 + 3 + r) * BLOCK];
-            }
-            if constexpr (dof_is_prismatic<M>(d)) {
-                gd = dot3(nrm, a);
-            } else {
-                const float rr[3] = {Cw[0] - o[0], Cw[1] - o[1], Cw[2] - o[2]};
-                float v[3];
-                cross3(a, rr, v);
-                gd = dot3(nrm, v);
-            }
-        }
-        g[d] = gd;
-    });
+    capsule_cuboid_gradient_core<M, BLOCK>(sm, tb.cap_frame[c], Cw, nrm, g);
 }
 
 }  // namespace cppflow
