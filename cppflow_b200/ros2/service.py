@@ -7,6 +7,7 @@ Same checks, in the same order, with the same messages and response fields; requ
 transport hands in (rclpy messages, or any object with those attributes).  Differences, all on the side of doing more:
 the obstacles of the environment message are USED (the reference stores them and plans without them, its own TODO at
 :166): cuboid obstacles reach the Problem and with them the capsule collision checks and the LM collision terms."""
+import math
 import traceback
 from dataclasses import replace
 from time import time
@@ -32,7 +33,7 @@ _BASE_LINK = {"fetch": "base_link", "fetch_arm": "torso_lift_link", "panda": "pa
 
 
 def _cuboid_obstacles(obstacles, device):
-    """Environment-message obstacles -> (list of (x, y, z, sx, sy, sz), Tcuboids, cuboids) in the layout of
+    """Environment-message obstacles -> (problem-file style dicts, Tcuboids, cuboids) in the layout of
     data_type_utils.py:109-127.  An obstacle is anything with .position (x, y, z) and .size (x, y, z) - axis-aligned
     cuboids, the only obstacle type the reference's problems use; an optional .orientation (w, x, y, z) rotates it."""
     specs, Tcuboids, cuboids = [], [], []
@@ -42,6 +43,7 @@ def _cuboid_obstacles(obstacles, device):
         assert min(sx, sy, sz) > 0, "obstacle sizes must be positive"
         Tc = torch.zeros((4, 4), dtype=torch.float32)
         Tc[:3, :3] = torch.eye(3)
+        roll = pitch = yaw = 0.0
         q = getattr(ob, "orientation", None)
         if q is not None:
             w, x, y, z = (float(getattr(q, a)) for a in "wxyz")
@@ -51,8 +53,12 @@ def _cuboid_obstacles(obstacles, device):
             Tc[:3, :3] = torch.tensor([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
                                        [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
                                        [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+            roll = math.atan2(2 * (w * x + y * z), 1 - 2 * (x * x + y * y))
+            pitch = math.asin(max(-1.0, min(1.0, 2 * (w * y - z * x))))
+            yaw = math.atan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z))
         Tc[0, 3], Tc[1, 3], Tc[2, 3] = px, py, pz
-        specs.append((px, py, pz, sx, sy, sz))
+        specs.append({"x": px, "y": py, "z": pz, "size_x": sx, "size_y": sy, "size_z": sz, "roll": roll, "pitch": pitch,
+                      "yaw": yaw})
         Tcuboids.append(Tc.to(device))
         cuboids.append(torch.tensor([-sx / 2, -sy / 2, -sz / 2, sx / 2, sy / 2, sz / 2], dtype=torch.float32, device=device))
     return specs, Tcuboids, cuboids

@@ -87,7 +87,8 @@ def test_planning_query_end_to_end():
     from cppflow_b200.data_type_utils import problem_from_filename
 
     ref = problem_from_filename(None, "fetch__circle", device="cuda:0")
-    obstacles = [NS(position=NS(x=o[0], y=o[1], z=o[2]), size=NS(x=o[3], y=o[4], z=o[5])) for o in ref.obstacles]
+    obstacles = [NS(position=NS(x=o["x"], y=o["y"], z=o["z"]), size=NS(x=o["size_x"], y=o["size_y"], z=o["size_z"]))
+                 for o in ref.obstacles]
     svc = CppFlowQueryService(device="cuda:0")
     assert svc.environment_setup(_env_request(obstacles=obstacles), NS()).success
     wp = [_pose(r) for r in ref.target_path.cpu().tolist()]
