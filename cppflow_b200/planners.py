@@ -85,6 +85,7 @@ class LatentIkSolver:
         lim = torch.tensor(robot.actuated_joints_limits, dtype=torch.float32)
         self._mid, self._half = lim.mean(dim=1), (lim[:, 1] - lim[:, 0]) / 2
         self._schedules: Dict = {}
+        self._donors: Dict = {}
         self.last_converged: Optional[torch.Tensor] = None
 
     # latent <-> seed configuration (the role of the flow's forward / reverse pass, planners.py:174-189)
@@ -127,6 +128,14 @@ class LatentIkSolver:
         err, _ = ops.pose_errors(self.robot.robot_id, self.robot.ndof, x, targets)
         return (err[:, 3:].norm(dim=1) < 1e-4) & (err[:, :3].norm(dim=1) < 1.745e-3)
 
+    def _donor_scores(self, k: int, dev) -> torch.Tensor:
+        """Fixed random preference matrix [k, k] (row p: which converged path p continues on when its own branch ends),
+        drawn once per k from a seeded host generator: candidate sets are reproducible run to run."""
+        key = (k, str(dev))
+        if key not in self._donors:
+            self._donors[key] = torch.rand((k, k), generator=torch.Generator().manual_seed(20240613)).to(dev)
+        return self._donors[key]
+
     def solve_paths(self, ee_path: torch.Tensor, latents: torch.Tensor, generator: Optional[torch.Generator] = None,
                     n_restarts: int = 3) -> torch.Tensor:
         """ee_path [T, 7], latents [k, network_width] -> [k, T, ndof]; `self.last_converged` = bool [k, T].
@@ -162,7 +171,7 @@ class LatentIkSolver:
             ok_alt = self._converged(alt, ee_path[t:t + 1])
             cur = torch.where(ok[:, None], cur, alt)
             ok = ok | ok_alt
-            donor = (torch.rand((k, k), device=dev) * ok[None, :]).argmax(dim=1)
+            donor = (self._donor_scores(k, dev) * ok[None, :]).argmax(dim=1)
             cur = torch.where(ok[:, None], cur, cur[donor])
             x[:, t] = cur
         for ni, li, ri, w in levels:

@@ -4,7 +4,10 @@ from cppflow_b200.data_type_utils import problem_from_filename, ALL_PROBLEM_FILE
 from cppflow_b200.data_types import PlannerSettings
 from cppflow_b200.planners import CppFlowPlanner, LatentIkCandidateGenerator, LmIkCandidateGenerator
 dev = torch.device("cuda:0")
-for label, kw, gen in (("rerun on large mjac", dict(do_rerun_if_large_dp_search_mjac=True), lambda s: LatentIkCandidateGenerator(seed=s)),
+for label, kw, gen in (("reference ROS settings (rerun on large mjac and on failure)",
+                        dict(do_rerun_if_large_dp_search_mjac=True, do_rerun_if_optimization_fails=True),
+                        lambda s: LatentIkCandidateGenerator(seed=s)),
+                       ("rerun on large mjac", dict(do_rerun_if_large_dp_search_mjac=True), lambda s: LatentIkCandidateGenerator(seed=s)),
                        ("no rerun", dict(), lambda s: LatentIkCandidateGenerator(seed=s))):
     for seed in (1, 2, 3, 4):
         nv, bad, t_tot = 0, [], 0.0
