@@ -29,6 +29,53 @@ __host__ __device__ constexpr float cap_half_length(int c) {
 // (|diff| ~ 1e-8), so the same rule needs a threshold above that noise: 1 micrometre.
 #define CPPFLOW_AXIS_INSIDE_D2 1e-12f
 
+// ----------------------------------------------------------------------------------------------------------------
+// The per-thread shared-memory column: world capsule endpoints, joint origins and joint axes of ONE configuration (slot k
+// of thread tid at sm[k * BLOCK + tid]: conflict-free).  On a serial arm most capsule endpoints ARE joint origins (a
+// capsule starts at its link frame's origin = the origin of the joint before it, and ends at the origin of the joint
+// after it): such an endpoint gets no slot of its own, its capsule reads the joint's origin slot.  The two values are
+// the same bits - the FK adds the next element's fixed translation with the same fmaf sequence capsule_endpoint uses.
+// Fetch: 13 of 20 endpoints alias (102 -> 69 floats per thread with joints, 60 -> 45 without); Panda: none.
+template <class M>
+struct SmemLayout {
+    // dof whose joint origin IS endpoint e of capsule c, or -1
+    static __host__ __device__ constexpr int alias(int c, int e) {
+        const int f = M::cap_frame(c);
+        const float x = M::cap(c, 3 * e), y = M::cap(c, 3 * e + 1), z = M::cap(c, 3 * e + 2);
+        if (f >= 1 && f <= M::NCHAIN && M::jtype(f - 1) == J_REVOLUTE && x == 0.f && y == 0.f && z == 0.f)
+            return dof_of_chain<M>(f - 1);  // the link frame's origin: a revolute joint does not move it
+        if (f < M::NCHAIN && M::jtype(f) != J_FIXED && x == M::origin(f, 0) && y == M::origin(f, 1) && z == M::origin(f, 2))
+            return dof_of_chain<M>(f);      // the next joint's origin (taken before a prismatic joint's displacement)
+        return -1;
+    }
+    static __host__ __device__ constexpr int n_own() {
+        int n = 0;
+        for (int c = 0; c < M::NCAP; ++c)
+            for (int e = 0; e < 2; ++e) n += alias(c, e) < 0 ? 1 : 0;
+        return n;
+    }
+    static constexpr bool ANY_ALIAS = n_own() < 2 * M::NCAP;
+    static constexpr int ORIGINS = n_own() * 3;              // joint d origin r: ORIGINS + d*3 + r
+    static constexpr int AXES = ORIGINS + M::NDOF * 3;       // joint d axis r:   AXES + d*3 + r
+    static constexpr int N_DIST = ANY_ALIAS ? AXES : ORIGINS;  // floats per thread when only distances are needed
+    static constexpr int N_FULL = AXES + M::NDOF * 3;
+    // slot of the x coordinate of endpoint e of capsule c
+    static __host__ __device__ constexpr int slot(int c, int e) {
+        const int a = alias(c, e);
+        if (a >= 0) return ORIGINS + a * 3;
+        int n = 0;
+        for (int cc = 0; cc < M::NCAP; ++cc)
+            for (int ee = 0; ee < 2; ++ee) {
+                if (cc == c && ee == e) return n * 3;
+                n += alias(cc, ee) < 0 ? 1 : 0;
+            }
+        return -1;
+    }
+    static __host__ __device__ constexpr int slots(int c) { return slot(c, 0) | (slot(c, 1) << 16); }  // P | Q << 16
+};
+static_assert(SmemLayout<Fetch>::N_FULL == 69 && SmemLayout<Fetch>::N_DIST == 45, "Fetch: 13 of 20 endpoints are joint origins");
+static_assert(!SmemLayout<Panda>::ANY_ALIAS && SmemLayout<Panda>::N_DIST == 54, "Panda: every endpoint has its own slot");
+
 template <class M>
 struct PairTable {
     int a[M::NPAIR];
@@ -54,6 +101,7 @@ __host__ __device__ constexpr PairTable<M> make_pair_table() {
 template <class M>
 struct CapTable {
     int frame[M::NCAP];
+    int slots[M::NCAP];  // SmemLayout::slots
     float radius[M::NCAP];
     float reach[M::NCAP];  // half-length + radius + margin
 };
@@ -62,6 +110,7 @@ __host__ __device__ constexpr CapTable<M> make_cap_table() {
     CapTable<M> t{};
     for (int c = 0; c < M::NCAP; ++c) {
         t.frame[c] = M::cap_frame(c);
+        t.slots[c] = SmemLayout<M>::slots(c);
         t.radius[c] = M::cap(c, 6);
         t.reach[c] = M::cap(c, 6) + cap_half_length<M>(c) + CPPFLOW_CULL_MARGIN;
     }
@@ -72,13 +121,24 @@ __constant__ PairTable<M> c_pair_table = make_pair_table<M>();
 template <class M>
 __constant__ CapTable<M> c_cap_table = make_cap_table<M>();
 
-template <class M>
-struct SmemLayout {
-    static constexpr int CAPS = 0;                 // capsule c endpoint e coordinate r: CAPS + c*6 + e*3 + r
-    static constexpr int JOINTS = M::NCAP * 6;     // joint d axis r: JOINTS + d*6 + r ; origin r: JOINTS + d*6 + 3 + r
-    static constexpr int N_DIST = M::NCAP * 6;     // floats per thread when only distances are needed
-    static constexpr int N_FULL = M::NCAP * 6 + M::NDOF * 6;
-};
+// shared by the FK sinks: joint origins go to the column when anything reads them (Jacobian columns, or capsule
+// endpoints that alias them), axes only with WITH_JOINTS; a capsule endpoint is stored unless it aliases a joint origin
+template <class M, int BLOCK, bool WITH_JOINTS, int D>
+__device__ __forceinline__ void store_joint(float* sm, const float* axis, const float* origin) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        if constexpr (WITH_JOINTS) sm[(SmemLayout<M>::AXES + D * 3 + r) * BLOCK] = axis[r];
+        if constexpr (WITH_JOINTS || SmemLayout<M>::ANY_ALIAS) sm[(SmemLayout<M>::ORIGINS + D * 3 + r) * BLOCK] = origin[r];
+    }
+}
+template <class M, int BLOCK, int C>
+__device__ __forceinline__ void store_capsule(float* sm, const float (&P)[3], const float (&Q)[3]) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        if constexpr (SmemLayout<M>::alias(C, 0) < 0) sm[(SmemLayout<M>::slot(C, 0) + r) * BLOCK] = P[r];
+        if constexpr (SmemLayout<M>::alias(C, 1) < 0) sm[(SmemLayout<M>::slot(C, 1) + r) * BLOCK] = Q[r];
+    }
+}
 
 // FK sink writing world capsule endpoints (and optionally joint axes/origins) into the thread's smem column
 template <class M, int BLOCK, bool WITH_JOINTS>
@@ -86,13 +146,7 @@ struct CollisionSink {
     float* sm;  // smem base + tid
     template <int D>
     __device__ __forceinline__ void joint(std::integral_constant<int, D>, const float* axis, const float* origin) {
-        if constexpr (WITH_JOINTS) {
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                sm[(SmemLayout<M>::JOINTS + D * 6 + r) * BLOCK] = axis[r];
-                sm[(SmemLayout<M>::JOINTS + D * 6 + 3 + r) * BLOCK] = origin[r];
-            }
-        }
+        store_joint<M, BLOCK, WITH_JOINTS, D>(sm, axis, origin);
     }
     template <int F>
     __device__ __forceinline__ void frame(std::integral_constant<int, F>, const Frame& fr) {
@@ -102,22 +156,20 @@ struct CollisionSink {
                 float P[3], Q[3];
                 capsule_endpoint<M, c, 0>(fr, P);
                 capsule_endpoint<M, c, 1>(fr, Q);
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    sm[(c * 6 + r) * BLOCK] = P[r];
-                    sm[(c * 6 + 3 + r) * BLOCK] = Q[r];
-                }
+                store_capsule<M, BLOCK, c>(sm, P, Q);
             }
         });
     }
 };
 
+// endpoints of a capsule from its slot word (SmemLayout::slots: P | Q << 16)
 template <int BLOCK>
-__device__ __forceinline__ void load_capsule(const float* sm, int c, float (&P)[3], float (&Q)[3]) {
+__device__ __forceinline__ void load_capsule(const float* sm, int slots, float (&P)[3], float (&Q)[3]) {
+    const int sp = slots & 0xffff, sq = slots >> 16;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        P[r] = sm[(c * 6 + r) * BLOCK];
-        Q[r] = sm[(c * 6 + 3 + r) * BLOCK];
+        P[r] = sm[(sp + r) * BLOCK];
+        Q[r] = sm[(sq + r) * BLOCK];
     }
 }
 
@@ -128,10 +180,11 @@ __device__ __forceinline__ void load_capsule(const float* sm, int c, float (&P)[
 // signed distance of capsules a and b; C2 = closest point on the axis of b, nrm = unit vector from it to the closest
 // point on the axis of a
 template <int BLOCK>
-__device__ __forceinline__ float capsule_pair_core(const float* sm, int a, int b, float rsum, float (&C2)[3], float (&nrm)[3]) {
+__device__ __forceinline__ float capsule_pair_core(const float* sm, int slots_a, int slots_b, float rsum, float (&C2)[3],
+                                                   float (&nrm)[3]) {
     float P1[3], Q1[3], P2[3], Q2[3];
-    load_capsule<BLOCK>(sm, a, P1, Q1);
-    load_capsule<BLOCK>(sm, b, P2, Q2);
+    load_capsule<BLOCK>(sm, slots_a, P1, Q1);
+    load_capsule<BLOCK>(sm, slots_b, P2, Q2);
     float s, t;
     segseg_closest(P1, Q1, P2, Q2, s, t);
     float diff[3];
@@ -161,8 +214,8 @@ __device__ __forceinline__ void capsule_pair_gradient_core(const float* sm, int 
             float a[3], o[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                a[r] = sm[(SmemLayout<M>::JOINTS + d * 6 + r) * BLOCK];
-                o[r] = sm[(SmemLayout<M>::JOINTS + d * 6 + 3 + r) * BLOCK];
+                a[r] = sm[(SmemLayout<M>::AXES + d * 3 + r) * BLOCK];
+                o[r] = sm[(SmemLayout<M>::ORIGINS + d * 3 + r) * BLOCK];
             }
             if constexpr (dof_is_prismatic<M>(d)) {
                 gd = -dot3(nrm, a);
@@ -217,8 +270,8 @@ __device__ __forceinline__ void capsule_cuboid_gradient_core(const float* sm, in
             float a[3], o[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                a[r] = sm[(SmemLayout<M>::JOINTS + d * 6 + r) * BLOCK];
-                o[r] = sm[(SmemLayout<M>::JOINTS + d * 6 + 3 + r) * BLOCK];
+                a[r] = sm[(SmemLayout<M>::AXES + d * 3 + r) * BLOCK];
+                o[r] = sm[(SmemLayout<M>::ORIGINS + d * 3 + r) * BLOCK];
             }
             if constexpr (dof_is_prismatic<M>(d)) {
                 gd = dot3(nrm, a);
@@ -239,7 +292,7 @@ __device__ __forceinline__ void capsule_cuboid_gradient_core(const float* sm, in
 template <class M, int BLOCK>
 __device__ __forceinline__ float self_pair_distance(const float* sm, int p, float (&C2)[3], float (&nrm)[3],
                                                     float cull_thr = INFINITY) {
-    const int a = c_pair_table<M>.a[p], b = c_pair_table<M>.b[p];
+    const int a = c_cap_table<M>.slots[c_pair_table<M>.a[p]], b = c_cap_table<M>.slots[c_pair_table<M>.b[p]];
     {
         float P1[3], Q1[3], P2[3], Q2[3];
         load_capsule<BLOCK>(sm, a, P1, Q1);
@@ -261,7 +314,7 @@ template <class M, int BLOCK>
 __device__ __forceinline__ float env_capsule_distance(const float* sm, int c, const Obstacles& ob, int o,
                                                       float (&Cw)[3], float (&nrm)[3], float cull_thr = INFINITY) {
     float P[3], Q[3], A[3], B[3];
-    load_capsule<BLOCK>(sm, c, P, Q);
+    load_capsule<BLOCK>(sm, c_cap_table<M>.slots[c], P, Q);
     to_box_frame(ob, o, P, A);
     to_box_frame(ob, o, Q, B);
     {
@@ -300,6 +353,7 @@ struct CollTables {
     int pair_ab[M::NPAIR];      // a | b << 8 | frame(a) << 16 | frame(b) << 24
     float pair_rsum[M::NPAIR];
     int cap_frame[M::NCAP];
+    int cap_slots[M::NCAP];     // SmemLayout::slots
     float cap_radius[M::NCAP];
     Obstacles ob;
 };
@@ -313,6 +367,7 @@ __device__ __forceinline__ void fill_coll_tables(CollTables<M>& tb, const Obstac
     }
     for (int c = tid; c < M::NCAP; c += nthreads) {
         tb.cap_frame[c] = c_cap_table<M>.frame[c];
+        tb.cap_slots[c] = c_cap_table<M>.slots[c];
         tb.cap_radius[c] = c_cap_table<M>.radius[c];
     }
     const int* src = reinterpret_cast<const int*>(&ob);
@@ -327,13 +382,7 @@ struct MidSink {
     float mid2[M::NCAP][3];
     template <int D>
     __device__ __forceinline__ void joint(std::integral_constant<int, D>, const float* axis, const float* origin) {
-        if constexpr (WITH_JOINTS) {
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                sm[(SmemLayout<M>::JOINTS + D * 6 + r) * BLOCK] = axis[r];
-                sm[(SmemLayout<M>::JOINTS + D * 6 + 3 + r) * BLOCK] = origin[r];
-            }
-        }
+        store_joint<M, BLOCK, WITH_JOINTS, D>(sm, axis, origin);
     }
     template <int F>
     __device__ __forceinline__ void frame(std::integral_constant<int, F>, const Frame& fr) {
@@ -343,12 +392,9 @@ struct MidSink {
                 float P[3], Q[3];
                 capsule_endpoint<M, c, 0>(fr, P);
                 capsule_endpoint<M, c, 1>(fr, Q);
+                store_capsule<M, BLOCK, c>(sm, P, Q);
 #pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    sm[(c * 6 + r) * BLOCK] = P[r];
-                    sm[(c * 6 + 3 + r) * BLOCK] = Q[r];
-                    mid2[c][r] = P[r] + Q[r];
-                }
+                for (int r = 0; r < 3; ++r) mid2[c][r] = P[r] + Q[r];
             }
         });
     }
@@ -454,7 +500,7 @@ template <class M, int BLOCK>
 __device__ __forceinline__ float self_pair_exact(const float* sm, const CollTables<M>& tb, int p, float (&C2)[3],
                                                  float (&nrm)[3]) {
     const int ab = tb.pair_ab[p];
-    return capsule_pair_core<BLOCK>(sm, ab & 0xff, (ab >> 8) & 0xff, tb.pair_rsum[p], C2, nrm);
+    return capsule_pair_core<BLOCK>(sm, tb.cap_slots[ab & 0xff], tb.cap_slots[(ab >> 8) & 0xff], tb.pair_rsum[p], C2, nrm);
 }
 template <class M, int BLOCK>
 __device__ __forceinline__ void self_pair_gradient_rt(const float* sm, const CollTables<M>& tb, int p,
@@ -466,7 +512,7 @@ template <class M, int BLOCK>
 __device__ __forceinline__ float env_capsule_exact(const float* sm, const CollTables<M>& tb, int c, int o,
                                                    float (&Cw)[3], float (&nrm)[3]) {
     float P[3], Q[3], A[3], B[3];
-    load_capsule<BLOCK>(sm, c, P, Q);
+    load_capsule<BLOCK>(sm, tb.cap_slots[c], P, Q);
     to_box_frame(tb.ob, o, P, A);
     to_box_frame(tb.ob, o, Q, B);
     return capsule_cuboid_core<BLOCK>(P, Q, A, B, tb.ob, o, tb.cap_radius[c], Cw, nrm);

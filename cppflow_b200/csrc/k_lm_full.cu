@@ -209,8 +209,8 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
             float a[3], o[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                a[r] = sm[(SmemLayout<M>::JOINTS + d * 6 + r) * ABLOCK];
-                o[r] = sm[(SmemLayout<M>::JOINTS + d * 6 + 3 + r) * ABLOCK];
+                a[r] = sm[(SmemLayout<M>::AXES + d * 3 + r) * ABLOCK];
+                o[r] = sm[(SmemLayout<M>::ORIGINS + d * 3 + r) * ABLOCK];
             }
             if constexpr (dof_is_prismatic<M>(d)) {
                 J[0][d] = 0.f; J[1][d] = 0.f; J[2][d] = 0.f;
@@ -1015,7 +1015,10 @@ static int launch_assemble(const cppflow_lm_params* p, const float* q, const flo
     AssembleParams ap;
     SolveParams sp;
     make_params<M>(p, ob.n, 0, ap, sp);
-    const size_t sh = sizeof(float) * ABLOCK * SmemLayout<M>::N_FULL;
+    size_t sh = sizeof(float) * ABLOCK * SmemLayout<M>::N_FULL;
+    // experiment switch (profiles/r02_notes.md, occupancy curve): extra KB of shared memory per CTA, e.g. 90 -> one CTA per SM
+    static const char* pad_kb = std::getenv("CPPFLOW_ASM_SMEM_PAD_KB");
+    if (pad_kb) sh += (size_t)std::atoi(pad_kb) * 1024;
     static SmemGrant granted;  // per template instantiation and device
     if (int rc = ensure_dynamic_smem(lm_assemble_kernel<M>, sh, granted)) return rc;
     const dim3 grid(grid_for(P, ABLOCK), (unsigned)T);
