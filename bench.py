@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--paths", type=int, default=8192)
     ap.add_argument("--waypoints", type=int, default=300)
-    ap.add_argument("--chunks", type=int, default=4, help="path chunks (streams) of the pipelined LM iterations")
+    ap.add_argument("--chunks", type=int, default=0, help="path chunks (streams) of the pipelined LM iterations (0: ResidentPipeline's choice)")
     ap.add_argument("--cpu-sample-paths", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -274,6 +274,8 @@ def plan_latency_cpu(problem, qs, schedule):
 
 
 def workload_config(args, n_gpus):
+    if not args.chunks:  # ResidentPipeline's own choice (the reference arm reports the same configuration)
+        args.chunks = max(4, min(6, args.paths // 1280))
     return {
         "workload": f"synthetic {args.paths} paths x {args.waypoints} waypoints Fetch 8-DOF, one fused LM iteration "
                     "(pose + differencing + virtual configs + self/env capsule collisions) + clamp; 4 fetch__circle cuboids",
@@ -381,7 +383,8 @@ def main():
 
     # the K timed iterations run chunk-pipelined: the path set is cut into `--chunks` chunks with one stream each, and
     # the block solve of one chunk runs under the assembly of another (pipeline.ResidentPipeline, CPPFLOW_LM_OVERLAP)
-    rpipe = ResidentPipeline(problem, P, all_terms_parameters(), n_chunks=args.chunks)
+    rpipe = ResidentPipeline(problem, P, all_terms_parameters(), n_chunks=args.chunks or None)
+    args.chunks = len(rpipe.chunks)
     metrics = torch.empty((P, 8), device=dev, dtype=torch.float32)
 
     def argmin_tail():
@@ -415,7 +418,7 @@ def main():
     for n_paths in sizes:
         s0, _ = shard_range(P, rank % max(1, P // n_paths), max(1, P // n_paths))
         xs = x0[s0 * T:(s0 + n_paths) * T]
-        pipe_s = ResidentPipeline(problem, n_paths, all_terms_parameters(), n_chunks=args.chunks)
+        pipe_s = ResidentPipeline(problem, n_paths, all_terms_parameters())
         time_pipeline(pipe_s, xs, x_out[: n_paths * T], warmup, barrier)
         per_size[n_paths] = max_over_ranks(time_pipeline(pipe_s, xs, x_out[: n_paths * T], steps, barrier)[0]) / steps
         del pipe_s

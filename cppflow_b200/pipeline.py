@@ -235,7 +235,7 @@ class ResidentPipeline:
     Chunks are multiples of 256 paths (the assembly CTA) where P allows."""
 
     def __init__(self, problem: Problem, n_paths: int, params: Optional[OptimizationParameters] = None,
-                 n_chunks: int = 4, device=None, overlap: bool = True, solve_sms: Optional[int] = None):
+                 n_chunks: Optional[int] = None, device=None, overlap: bool = True, solve_sms: Optional[int] = None):
         """`solve_sms`: instead of sharing SMs, give the block solves `solve_sms` SMs of their own (a green-context
         partition) and the assembly the rest: the solves then run at their stand-alone speed and displace nothing."""
         self.problem = problem
@@ -245,6 +245,10 @@ class ResidentPipeline:
         self.device = problem.target_path.device if device is None else torch.device(device)
         self.prm = ops.make_params(params if params is not None else all_terms_parameters())
         self.overlap = overlap
+        if n_chunks is None:
+            # measured at T = 300 (K = 20, ms per iteration): 8192 paths 4 / 6 / 8 chunks 0.518 / 0.509 / 0.516; 4096 paths
+            # 4 / 6 chunks 0.37 / 0.41; 2048 paths 0.28 / 0.34 - a chunk below ~1000 paths no longer fills the SMs
+            n_chunks = max(4, min(6, n_paths // 1280))
         self.chunks = split_paths(n_paths, n_chunks)
         self.partition = None
         if solve_sms:
@@ -295,11 +299,18 @@ class ResidentPipeline:
                                                     ops.ptr(out[sl]), ss.cuda_stream))
                 self.ev_solve[c].record(ss)
             return
-        for (p0, n), s, ws in zip(self.chunks, self.streams, self.ws):
-            sl = slice(p0 * T, (p0 + n) * T)
-            with torch.cuda.stream(s):
-                ops.lm_full_step(rid, D, self.prm, x[sl], None, self.problem.target_path, n, T,
-                                 self.problem.obstacle_tables, clamp, out=out[sl], overlap=self.overlap, workspace=ws)
+        # straight through the C ABI on each chunk's stream (the ops wrapper costs ~20 us of host time per call: with six
+        # chunks that is a quarter of the step)
+        lib = ops._lib.load()
+        cu, tc, no = ops._obs(self.problem.obstacle_tables)
+        flags = (ops.LM_CLAMP if clamp else 0) | (ops.LM_OVERLAP if self.overlap else 0)
+        assert x.is_cuda and out.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
+        tgt = ops.ptr(self.problem.target_path)
+        with torch.cuda.device(self.device):
+            for (p0, n), s, ws in zip(self.chunks, self.streams, self.ws):
+                sl = slice(p0 * T, (p0 + n) * T)
+                ops.check(lib.cppflow_lm_full_step(rid, self.prm, ops.ptr(x[sl]), None, tgt, n, T, cu, tc, no, flags,
+                                                   ops.ptr(ws), ws.numel(), ops.ptr(out[sl]), s.cuda_stream))
 
     def enqueue_metrics(self, x: torch.Tensor, metrics: torch.Tensor, sign_only: bool = True):
         """Per-path validity metrics of x ([P*T, D]) into `metrics` ([P, 8]), each chunk's rows on the chunk's own stream
