@@ -17,7 +17,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-std=c++17", "-O3", "-lineinfo", "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC",
-]
+] + (["-DCPPFLOW_SOLVE_TIMING"] if os.environ.get("CPPFLOW_SOLVE_TIMING") else [])  # debug build: tools/probe_solve_phases.py
 
 
 def _nvcc():

@@ -403,9 +403,56 @@ struct BetaSel {
     }
 };
 
+#ifdef CPPFLOW_SOLVE_TIMING
+// debug build only (tools/probe_solve_phases.py): cycles of lane 0 of every warp per phase of the forward / backward loops
+__device__ unsigned long long g_solve_cycles[8];
+#define PHASE_T(var) const long long var = clock64()
+#define PHASE_DECL long long ph_acc[7] = {0, 0, 0, 0, 0, 0, 0}
+#define PHASE_ADD(i, a, b) ph_acc[i] += (b) - (a)
+#define PHASE_FLUSH if (lane == 0) { for (int i_ = 0; i_ < 7; ++i_) atomicAdd(&g_solve_cycles[i_], (unsigned long long)ph_acc[i_]); }
+extern "C" int cppflow_debug_solve_cycles(unsigned long long* h_out, int reset) {
+    if (reset) { unsigned long long z[8] = {}; cudaMemcpyToSymbol(g_solve_cycles, z, sizeof(z)); return 0; }
+    cudaMemcpyFromSymbol(h_out, g_solve_cycles, sizeof(unsigned long long) * 8);
+    return 0;
+}
+#else
+#define PHASE_T(var)
+#define PHASE_DECL
+#define PHASE_ADD(i, a, b)
+#define PHASE_FLUSH
+#endif
+
+// shared-space (32-bit) address forms of the ring primitives: the ring bookkeeping below runs once per step on the
+// critical path of a latency-bound chain, so it is kept to 32-bit adds on precomputed bases (no generic -> shared
+// conversions, no 64-bit index arithmetic, no modulo)
+__device__ __forceinline__ void mbar_expect_tx_a(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_a(unsigned dst, const void* gmem, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(gmem), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async16_a(unsigned dst, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4_a(unsigned dst, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gmem) : "memory");
+}
+
 template <class M, int SOLVE_RING, int SOLVE_WARPS>
 __global__ void __launch_bounds__(32 * SOLVE_WARPS, 512 / (32 * SOLVE_WARPS))
-lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const SolveParams prm, float* __restrict__ ws,
+lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T64, const SolveParams prm, float* __restrict__ ws,
                       float* __restrict__ x_out) {
     constexpr int D = M::NDOF;
     constexpr int NT = BlockLayout<D>::NT;
@@ -413,44 +460,65 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
     constexpr int NV = NW / 4;
     using SM = SolveSmem<D, SOLVE_RING>;
     extern __shared__ __align__(128) unsigned char smem_all[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the warp index as a value ptxas KNOWS to be warp-uniform (a shuffle from lane 0): everything derived from it - the
+    // group's workspace base, the ring and barrier addresses - then lives in uniform registers, and a TMA issue is one
+    // UBLKCP.  With threadIdx.x >> 5 each UBLKCP was wrapped in an ELECT + 4 x R2UR.BROADCAST + BRA.U.ANY loop (the
+    // compiler's fallback for possibly divergent operands): ~100 cycles per copy, twice per step of a latency-bound chain.
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int64_t g = (int64_t)blockIdx.x * SOLVE_WARPS + warp;  // 16-path group of this warp
     __shared__ uint64_t s_bars[SOLVE_WARPS][SOLVE_RING];  // one mbarrier per load slot
-    uint64_t* bars = s_bars[warp];
     if (lane == 0) {
 #pragma unroll
-        for (int j = 0; j < SOLVE_RING; ++j) mbar_init(bars + j);
+        for (int j = 0; j < SOLVE_RING; ++j) mbar_init(s_bars[warp] + j);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();          // the only block-level synchronisation: warps are independent from here on
     if (g * 16 >= P) return;
+    const int T = (int)T64;   // <= 65535 (check_common): waypoint indices are 32-bit from here on
     unsigned char* sm = smem_all + (size_t)warp * SM::BYTES;
+    const unsigned sm_a = smem_u32(sm);              // shared-space address of this warp's ring ...
+    const unsigned bar_a = smem_u32(s_bars[warp]);   // ... and of its mbarriers (8 bytes apart)
     const int side = lane & 1, l = lane >> 1;
     const int64_t p_raw = g * 16 + l;
     const bool active = p_raw < P;
     const int64_t p = active ? p_raw : P - 1;  // idle lanes (P % 16 != 0) work on the group's padding and never store x
-    unsigned char* wsg = reinterpret_cast<unsigned char*>(ws) + g * T * SM::BLK_BYTES;  // block t at wsg + t * BLK_BYTES
-    const float* qp = q + p * T * D;
-    const int64_t m = T / 2;
-    const int64_t n0 = m, n1 = T - 1 - m;           // blocks eliminated by side 0 / side 1
-    const int64_t n_side = side == 0 ? n0 : n1;
-    const int64_t n_iter = n0 > n1 ? n0 : n1;
+    unsigned char* wsg = reinterpret_cast<unsigned char*>(ws) + g * T64 * SM::BLK_BYTES;  // block t at wsg + t * BLK_BYTES
+    const float* qp = q + p * T64 * D;
+    float* xp = x_out + p * T64 * D;
+    const int m = T / 2;
+    const int n0 = m, n1 = T - 1 - m;           // blocks eliminated by side 0 / side 1
+    const int n_side = side == 0 ? n0 : n1;
+    const int n_iter = n0 > n1 ? n0 : n1;
     const BetaSel<M> bs(prm.b_rev, prm.b_pri);
 
-    // lane 0: arm slot (s % RING) and fetch the blocks t0 (side 0) / t1 (side 1); a negative t skips that side
+    // Ring state: step s (0 .. 2 n_iter - 1: elimination, then back-substitution) lives in slot s % RING and completes
+    // that slot's barrier for the (s / RING)-th time - kept as a running (slot, phase) pair instead of a modulo and a
+    // division per step.
+    int slot = 0;
+    unsigned phase = 0u;
+    auto advance = [&]() {
+        if (++slot == SOLVE_RING) { slot = 0; phase ^= 1u; }
+    };
+    // Arm slot `sl` and fetch the blocks t0 (side 0) / t1 (side 1) of a later step into it; a negative t skips that
+    // side.  Addresses are computed by every lane (cheap, off the elected lane's serial path); lane 0 issues.
     // `token` is the (always zero, but opaque to the compiler) value of slot_read_token below: folding it into the
     // destination address makes the refill of a slot data-dependent on the completed shared-memory reads of its
-    // previous contents
-    auto issue_step = [&](int64_t s, int64_t t0, int64_t t1, unsigned token = 0u) {
-        const int slot = (int)(s % SOLVE_RING);
-        unsigned char* dst = sm + (size_t)slot * SM::SLOT_BYTES + token;
-        mbar_expect_tx(bars + slot, (unsigned)SM::BLK_BYTES * ((t0 >= 0) + (t1 >= 0)));
-        if (t0 >= 0) bulk_g2s(SM::part(dst, 0), wsg + t0 * SM::BLK_BYTES, SM::BLK_BYTES, bars + slot);
-        if (t1 >= 0) bulk_g2s(SM::part(dst, 1), wsg + t1 * SM::BLK_BYTES, SM::BLK_BYTES, bars + slot);
+    // previous contents.
+    auto issue = [&](int sl, int t0, int t1, unsigned token) {
+        const unsigned bar = bar_a + (unsigned)sl * 8u;
+        const unsigned dst = sm_a + (unsigned)sl * (unsigned)SM::SLOT_BYTES + token;
+        const unsigned tx = (unsigned)SM::BLK_BYTES * ((t0 >= 0 ? 1u : 0u) + (t1 >= 0 ? 1u : 0u));
+        const unsigned char* s0 = wsg + (t0 >= 0 ? t0 : 0) * SM::BLK_BYTES;
+        const unsigned char* s1 = wsg + (t1 >= 0 ? t1 : 0) * SM::BLK_BYTES;
+        if (lane == 0) {
+            mbar_expect_tx_a(bar, tx);
+            if (t0 >= 0) bulk_g2s_a(dst, s0, SM::BLK_BYTES, bar);
+            if (t1 >= 0) bulk_g2s_a(dst + (unsigned)(SM::BLK_BYTES + 64), s1, SM::BLK_BYTES, bar);
+        }
     };
-    auto wait_step = [&](int64_t s) { mbar_wait(bars + (int)(s % SOLVE_RING), (unsigned)((s / SOLVE_RING) & 1)); };
-    auto read_block = [&](int64_t s, float (&v)[NW]) {
-        unsigned char* part = SM::part(sm + (size_t)(s % SOLVE_RING) * SM::SLOT_BYTES, side);
+    auto wait_slot = [&]() { mbar_wait_a(bar_a + (unsigned)slot * 8u, phase); };
+    auto read_block = [&](float (&v)[NW]) {
+        unsigned char* part = SM::part(sm + slot * SM::SLOT_BYTES, side);
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             const float4 f = *SM::blk(part, k, l);
@@ -471,14 +539,14 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
         }
         return __reduce_or_sync(0xffffffffu, acc & prm.zero);  // prm.zero = 0 at run time: neither nvcc nor ptxas can fold it
     };
-    auto store_x = [&](int64_t t, float (&xn)[D]) {
+    auto store_x = [&](int t, float (&xn)[D]) {
         if (prm.do_clamp) {
             static_for<D>([&](auto Dd) {
                 constexpr int d = decltype(Dd)::value;
                 xn[d] = fminf(fmaxf(xn[d], dof_lower<M>(d)), dof_upper<M>(d));
             });
         }
-        float* xo = x_out + (p * T + t) * D;
+        float* xo = xp + t * D;
         if constexpr (D % 4 == 0) {
 #pragma unroll
             for (int d = 0; d < D; d += 4)
@@ -489,6 +557,7 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
         }
     };
 
+    PHASE_DECL;
     // running state of this side: nS = -S^-1 of the block eliminated last (packed lower triangle), u = S^-1 y
     float nS[NT], u[D];
 #pragma unroll
@@ -497,19 +566,20 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
     for (int d = 0; d < D; ++d) u[d] = 0.f;
 
     // ---- elimination sweep (steps s = 0 .. n_iter-1):  S_t = A_t + (beta beta^T) . nS,  y_t = b_t + beta . u_in
-    if (lane == 0) {
-        for (int64_t j = 0; j < SOLVE_RING && j < n_iter; ++j) issue_step(j, j < n0 ? j : -1, j < n1 ? T - 1 - j : -1);
-    }
-    for (int64_t k = 0; k < n_iter; ++k) {
+#pragma unroll
+    for (int j = 0; j < SOLVE_RING; ++j)
+        if (j < n_iter) issue(j, j < n0 ? j : -1, j < n1 ? T - 1 - j : -1, 0u);
+    for (int k = 0; k < n_iter; ++k) {
         const bool mine = k < n_side;
         float blk[NW];
-        wait_step(k);
-        if (mine) read_block(k, blk);
-        const unsigned token = slot_read_token(blk, mine);  // every lane's reads of the slot have returned: refill it
-        if (lane == 0) {
-            const int64_t j = k + SOLVE_RING;
-            if (j < n_iter) issue_step(j, j < n0 ? j : -1, j < n1 ? T - 1 - j : -1, token);
-        }
+        PHASE_T(c0);
+        wait_slot();
+        PHASE_T(c1);
+        if (mine) read_block(blk);
+        const unsigned token = slot_read_token(blk, mine);  // every lane's reads of the slot have returned
+        PHASE_T(c2);
+        PHASE_ADD(0, c0, c1);
+        PHASE_ADD(1, c1, c2);
         if (mine) {
             static_for<D>([&](auto Ii) {
                 constexpr int i = decltype(Ii)::value;
@@ -520,6 +590,14 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
                 });
             });
             sweep_neg_inverse<D>(nS, u, prm.pivot_floor);
+        }
+        PHASE_T(c3);
+        PHASE_ADD(2, c2, c3);
+        // refill the slot with step k + RING.  Issued AFTER the sweep: the elected lane's few instructions would
+        // otherwise sit between the loads and the first pivot of every step; the slot is not needed for RING more steps.
+        {
+            const int j = k + SOLVE_RING;
+            if (j < n_iter) issue(slot, j < n0 ? j : -1, j < n1 ? T - 1 - j : -1, token);
         }
         // block t <- (-S_t^-1 packed, u_t) with 16-byte generic stores: a warp instruction covers 256 contiguous bytes
         // per side.  (An earlier version staged the block in shared memory and sent it with a TMA bulk store: the
@@ -538,30 +616,41 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
 #pragma unroll
             for (int i = 0; i < NV; ++i) dstg[i * 16] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
+        PHASE_T(c4);
+        PHASE_ADD(3, c3, c4);
+        advance();
     }
+    PHASE_T(cf0);
     __threadfence();                                  // the generic stores above are performed ...
     asm volatile("fence.proxy.async;" ::: "memory");  // ... and ordered before the async-proxy (TMA) reads below
     __syncwarp();
 
     // ---- back-substitution loads (steps s = n_iter .. 2 n_iter - 1, block order k = n_side-1 ... 0) start while the
-    // middle block is factorised; they read what the bulk stores above wrote, so those have to be complete
-    auto issue_q = [&](int slot, int64_t t) {
+    // middle block is factorised; they read what the stores above wrote, so those have to be complete
+    const unsigned q_a = sm_a + (unsigned)SM::OFF_Q + (unsigned)lane * 16u;  // this lane's 16 bytes of q slot 0, dof group 0
+    auto issue_q = [&](int qs, int t) {
+        const float* src = qp + t * D;
+        const unsigned dst = q_a + (unsigned)qs * (unsigned)SM::Q_BYTES;
         if constexpr (D % 4 == 0) {
 #pragma unroll
-            for (int d = 0; d < D; d += 4) cp_async16(SM::qv(sm, slot, d, lane), qp + t * D + d);
+            for (int d = 0; d < D; d += 4) cp_async16_a(dst + (unsigned)(d >> 2) * 512u, src + d);
         } else {
 #pragma unroll
-            for (int d = 0; d < D; ++d) cp_async4(SM::qv(sm, slot, d, lane), qp + t * D + d);
+            for (int d = 0; d < D; ++d) cp_async4_a(dst + (unsigned)(d >> 2) * 512u + (unsigned)(d & 3) * 4u, src + d);
         }
     };
-    auto t_of = [&](int64_t k) { return side == 0 ? k : T - 1 - k; };
-    if (lane == 0) {
-        for (int64_t r = 0; r < SOLVE_RING && r < n_iter; ++r)
-            issue_step(n_iter + r, n0 - 1 - r >= 0 ? n0 - 1 - r : -1, n1 - 1 - r >= 0 ? T - 1 - (n1 - 1 - r) : -1);
+    auto t_of = [&](int k) { return side == 0 ? k : T - 1 - k; };
+    {
+        int sl = slot;  // the slots after the last elimination step, in ring order
+#pragma unroll
+        for (int r = 0; r < SOLVE_RING; ++r) {
+            if (r < n_iter) issue(sl, n0 - 1 - r >= 0 ? n0 - 1 - r : -1, n1 - 1 - r >= 0 ? T - 1 - (n1 - 1 - r) : -1, 0u);
+            if (++sl == SOLVE_RING) sl = 0;
+        }
     }
 #pragma unroll
     for (int r = 0; r < SOLVE_RING; ++r) {
-        const int64_t k = n_side - 1 - r;
+        const int k = n_side - 1 - r;
         if (k >= 0) issue_q(r, t_of(k));
         cp_async_commit();
     }
@@ -597,26 +686,24 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
     }
 
     // ---- back-substitution outwards from the middle: dx_t = u_t + S_t^-1 (beta . dx_inner) = u_t - nS_t (beta . dx_inner)
-    for (int64_t r = 0; r < n_iter; ++r) {
+    int qslot = 0;
+    for (int r = 0; r < n_iter; ++r) {
         cp_async_wait<SOLVE_RING - 1>();
-        const int64_t k = n_side - 1 - r;
+        const int k = n_side - 1 - r;
         const bool mine = k >= 0;
-        const int qslot = (int)(r % SOLVE_RING);
         float blk[NW], xn[D];
-        wait_step(n_iter + r);
+        PHASE_T(b0);
+        wait_slot();
+        PHASE_T(b1);
+        PHASE_ADD(4, b0, b1);
         if (mine) {
-            read_block(n_iter + r, blk);
+            read_block(blk);
 #pragma unroll
             for (int d = 0; d < D; ++d) xn[d] = *SM::qv(sm, qslot, d, lane);
         }
         const unsigned token = slot_read_token(blk, mine);
-        if (lane == 0) {
-            const int64_t rn = r + SOLVE_RING;
-            if (rn < n_iter)
-                issue_step(n_iter + rn, n0 - 1 - rn >= 0 ? n0 - 1 - rn : -1, n1 - 1 - rn >= 0 ? T - 1 - (n1 - 1 - rn) : -1, token);
-        }
         if (mine) {
-            const int64_t kn = k - SOLVE_RING;
+            const int kn = k - SOLVE_RING;
             if (kn >= 0) issue_q(qslot, t_of(kn));
             float z[D];
             static_for<D>([&](auto Ii) {
@@ -636,11 +723,23 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T, const S
             }
 #pragma unroll
             for (int i = 0; i < D; ++i) xn[i] += dx[i];
-            if (active) store_x(t_of(k), xn);
         }
+        {
+            const int rn = r + SOLVE_RING;  // refill after the arithmetic, as in the elimination
+            if (rn < n_iter)
+                issue(slot, n0 - 1 - rn >= 0 ? n0 - 1 - rn : -1, n1 - 1 - rn >= 0 ? T - 1 - (n1 - 1 - rn) : -1, token);
+        }
+        if (mine && active) store_x(t_of(k), xn);
         cp_async_commit();
+        PHASE_T(b2);
+        PHASE_ADD(5, b1, b2);
+        advance();
+        if (++qslot == SOLVE_RING) qslot = 0;
     }
     cp_async_wait<0>();
+    PHASE_T(cf1);
+    PHASE_ADD(6, cf0, cf1);  // fence + middle block + whole back-substitution
+    PHASE_FLUSH;
 }
 
 // ----------------------------------------------------------------------------------------------------------------
