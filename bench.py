@@ -275,7 +275,7 @@ def plan_latency_cpu(problem, qs, schedule):
 
 def workload_config(args, n_gpus):
     if not args.chunks:  # ResidentPipeline's own choice (the reference arm reports the same configuration)
-        args.chunks = max(4, min(6, args.paths // 1280))
+        args.chunks = 6 if args.paths >= 6144 else 1 if args.paths >= 3072 else 2 if args.paths >= 1536 else 4
     return {
         "workload": f"synthetic {args.paths} paths x {args.waypoints} waypoints Fetch 8-DOF, one fused LM iteration "
                     "(pose + differencing + virtual configs + self/env capsule collisions) + clamp; 4 fetch__circle cuboids",

@@ -246,10 +246,15 @@ class ResidentPipeline:
         self.prm = ops.make_params(params if params is not None else all_terms_parameters())
         self.overlap = overlap
         if n_chunks is None:
-            # measured at T = 300 (K = 20, ms per iteration): 8192 paths 4 / 6 / 8 chunks 0.518 / 0.509 / 0.516; 4096 paths
-            # 4 / 6 chunks 0.37 / 0.41; 2048 paths 0.28 / 0.34 - a chunk below ~1000 paths no longer fills the SMs
-            n_chunks = max(4, min(6, n_paths // 1280))
+            # measured at T = 300, K = 20 (tools/probe_timeline.py, ms per iteration by chunk count 1 / 2 / 3 / 4 / 6):
+            #   8192 paths: - / - / - / 0.518 / 0.509      4096: 0.387 / 0.407 / 0.416 / 0.422 / 0.415
+            #   2048: 0.302 / 0.282 / 0.303 / 0.310 / 0.348      1024: 0.245 / 0.231 / 0.288 / 0.194 / 0.201
+            # below ~6000 paths a chunk no longer fills the SMs and the iteration is the solve's chain latency: one or two
+            # chunks; at 1024 paths four chunks of 256 take the register-resident solve (ops / launch_solve)
+            n_chunks = 6 if n_paths >= 6144 else 1 if n_paths >= 3072 else 2 if n_paths >= 1536 else 4
         self.chunks = split_paths(n_paths, n_chunks)
+        if len(self.chunks) == 1:
+            self.overlap = False  # nothing to run under: the stand-alone solve variants are faster
         self.partition = None
         if solve_sms:
             self.partition = SmPartition(self.device, solve_sms, len(self.chunks), len(self.chunks))

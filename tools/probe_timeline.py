@@ -10,7 +10,7 @@ from cppflow_b200.lm_hyper_parameters import all_terms_parameters
 from cppflow_b200.pipeline import split_paths
 
 dev = torch.device("cuda:0"); lib = _lib.load()
-robot = get_robot("fetch"); P, T, D = 8192, 300, 8
+robot = get_robot("fetch"); P, T, D = int(os.environ.get("P", 8192)), 300, 8
 problem = synthetic_problem(robot, T, device=dev)
 x0 = synthetic_seeds_host(robot, P, T)[1].to(dev); xo = torch.empty_like(x0)
 rid = robot.robot_id; cu, tc, no = ops._obs(problem.obstacle_tables)
