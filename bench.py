@@ -711,7 +711,7 @@ def main():
                 "api": "cppflow_b200.pipeline.HostPipeline.refine_async(host x -> host x_new), pinned host buffers, "
                        "independent steps two deep in flight",
                 "ms_per_step_one_at_a_time": e2e_serial_ms},
-        "gpu_launches": steps * 2 * len(rpipe.chunks) + len(rpipe.chunks),
+        "gpu_launches": steps * 2 * len(rpipe.chunks) + len(rpipe.chunks) + 1,  # K x (assemble + solve) per chunk, metrics per chunk, key + argmin
         "ms_per_step_without_tail": ms_steps_only,
         "single_stream_ms_per_step": ms_single,
         "roofline": roofline,
