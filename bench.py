@@ -302,18 +302,32 @@ def emit(line: dict):
 _REAL_STDOUT = 1
 
 
+_GRAPHS = {}
+
+
 def time_pipeline(rpipe, x_in, x_out, steps, barrier, metrics=None, tail=None):
     """K pipelined steps (+ optionally each chunk's metrics and a tail enqueued on the current stream) between two CUDA
-    events with a barrier + device synchronisation on both sides.  -> (ms total, whatever `tail` returned)"""
+    events with a barrier + device synchronisation on both sides.  -> (ms total, whatever `tail` returned).
+    The K x chunks x (assemble, solve) launches (+ the metrics) are captured once into a CUDA graph and replayed: one
+    launch per timed region instead of hundreds of Python -> ctypes calls (with 8 ranks on 16 host cores the enqueue
+    loop's jitter otherwise shows up as skew in front of the all-gather)."""
+
+    def enqueue():
+        for _ in range(steps):
+            rpipe.enqueue_step(x_in, x_out)
+        if metrics is not None:
+            rpipe.enqueue_metrics(x_out, metrics)
+
+    key = (id(rpipe), x_in.data_ptr(), x_out.data_ptr(), steps, None if metrics is None else metrics.data_ptr())
+    if key not in _GRAPHS:
+        rpipe.begin(); enqueue(); rpipe.end()  # eager once: first calls set kernel attributes
+        torch.cuda.synchronize()
+        _GRAPHS[key] = (rpipe, rpipe.capture(enqueue))  # (the pipeline is kept alive with its graph)
+    graph = _GRAPHS[key][1]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    rpipe.begin()
-    for _ in range(steps):
-        rpipe.enqueue_step(x_in, x_out)
-    if metrics is not None:
-        rpipe.enqueue_metrics(x_out, metrics)
-    rpipe.end()
+    graph.replay()
     pending = tail() if tail is not None else None
     e1.record()
     barrier()
@@ -421,7 +435,6 @@ def main():
         pipe_s = ResidentPipeline(problem, n_paths, all_terms_parameters())
         time_pipeline(pipe_s, xs, x_out[: n_paths * T], warmup, barrier)
         per_size[n_paths] = max_over_ranks(time_pipeline(pipe_s, xs, x_out[: n_paths * T], steps, barrier)[0]) / steps
-        del pipe_s
     if world > 1:
         ms_strong = per_size[max(16, P // world)]
         strong = {"paths_total": P, "paths_per_gpu": max(16, P // world), "ms_per_step": ms_strong,

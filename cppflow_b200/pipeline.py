@@ -331,6 +331,18 @@ class ResidentPipeline:
                                                   cu, tc, no, ops.METRICS_SIGN_ONLY if sign_only else 0,
                                                   ops.ptr(metrics[p0:p0 + n]), s.cuda_stream))
 
+    def capture(self, enqueue) -> torch.cuda.CUDAGraph:
+        """CUDA graph of whatever `enqueue()` puts on the chunk streams between begin() and end() (steps, metrics): the
+        whole fork / launch / join pattern - 2 launches per chunk and step - then costs ONE graph launch instead of one
+        Python -> ctypes call per kernel, which matters when several ranks share a host's cores.  Run the same work
+        eagerly once before capturing (first calls set kernel attributes)."""
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.begin()
+            enqueue()
+            self.end()
+        return graph
+
     def iterate(self, x: torch.Tensor, n_iters: int, clamp: bool = True) -> torch.Tensor:
         """n_iters dependent LM iterations (x <- step(x)); returns the refined paths (a new tensor; x is kept)."""
         assert x.is_cuda and x.shape == (self.P * self.T, self.robot.ndof)

@@ -482,3 +482,38 @@ def test_native_key_argmin_matches_torch_keys(P, all_invalid):
     got = ops.path_key_argmin(md, C, first).cpu().tolist()
     assert got == want
     assert tuple(enqueue_argmin(md, C, first, 1).result()) == tuple(enqueue_argmin(m, C, first, 1).result())
+
+
+def test_resident_pipeline_graph_replay_equals_eager(robots):
+    """ResidentPipeline.capture: the chunk-pipelined iterations replayed from a CUDA graph give the bits of the eager
+    enqueue and of one single-stream step (chunks of 256 paths: register-resident solve; 300 paths: ragged)."""
+    from cppflow_b200 import ops
+    from cppflow_b200.lm_hyper_parameters import all_terms_parameters
+    from cppflow_b200.pipeline import ResidentPipeline
+    from cppflow_b200.synthetic import synthetic_problem as device_problem, synthetic_seeds_host
+
+    robot, T = robots["fetch"], 61
+    problem = device_problem(robot, T, seed=0, device=DEV)
+    prm = ops.make_params(all_terms_parameters())
+    for P, n_chunks in ((1024, None), (300, 3), (2048, None)):
+        x = synthetic_seeds_host(robot, P, T, seed=0)[1].to(DEV)
+        ref = ops.lm_full_step(robot.robot_id, robot.ndof, prm, x, None, problem.target_path, P, T, problem.obstacle_tables, True)
+        pipe = ResidentPipeline(problem, P, all_terms_parameters(), n_chunks=n_chunks)
+        out_e, out_g = torch.full_like(x, float("nan")), torch.full_like(x, float("nan"))
+        metrics = torch.zeros((P, 8), device=DEV)
+
+        def work(out):
+            for _ in range(3):
+                pipe.enqueue_step(x, out)
+            pipe.enqueue_metrics(out, metrics)
+
+        pipe.begin(); work(out_e); pipe.end()
+        torch.cuda.synchronize()
+        m_eager = metrics.clone()
+        graph = pipe.capture(lambda: work(out_g))
+        metrics.zero_()
+        for _ in range(2):
+            graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out_e, ref) and torch.equal(out_g, ref)
+        assert torch.equal(metrics, m_eager)
