@@ -104,7 +104,7 @@ class LmLoopJobC(C.Structure):
     ]
 
 
-ABI_VERSION = 2  # CPPFLOW_ABI_VERSION of include/cppflow_b200.h
+ABI_VERSION = 3  # CPPFLOW_ABI_VERSION of include/cppflow_b200.h
 
 _VP, _I, _I64, _SZ, _F, _DBL = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float, C.c_double
 _PROTOTYPES = {

@@ -83,7 +83,7 @@ const char* cppflow_last_error(void);
  * cppflow_robot_info, cppflow_constraints, cppflow_lm_loop_result, cppflow_lm_loop_job (as many as fit in n).
  * Returns the number of values the library knows (6).  A binding compares them with its own struct sizes after
  * dlopen and refuses a library built from another header. */
-#define CPPFLOW_ABI_VERSION 2
+#define CPPFLOW_ABI_VERSION 3
 int cppflow_abi_info(int64_t* out, int n);
 
 /* jrl.Robot properties (ndof, actuated_joints_limits, prismatic_joint_idxs, _collision_capsules_by_link). */
