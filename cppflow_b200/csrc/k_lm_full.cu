@@ -95,10 +95,77 @@ __device__ __forceinline__ float wrap_pi_lm(float d) {
     return fmaf(k, -6.28318548202514648f, d);  // float32(2 pi), the modulus torch uses
 }
 
+struct SolveParams {
+    float b_rev, b_pri;  // beta of revolute / prismatic dofs
+    float pivot_floor;   // lambda: every Schur complement of J^T J + lambda I has pivots >= lambda
+    int do_clamp;
+    unsigned zero;       // always 0; a run-time value so that dependency tokens built from it survive the optimisers
+};
+
+// beta of dof d / product beta_i beta_j with the prismatic pattern folded at compile time (three registers instead of
+// D (D + 1) / 2 products): beta_d = b_pri for prismatic dofs, b_rev otherwise (make_params)
 template <class M>
+struct BetaSel {
+    float b_rev, b_pri, rr, rp, pp;
+    __device__ __forceinline__ BetaSel(float b_rev_, float b_pri_)
+        : b_rev(b_rev_), b_pri(b_pri_), rr(b_rev_ * b_rev_), rp(b_rev_ * b_pri_), pp(b_pri_ * b_pri_) {}
+    template <int d>
+    __device__ __forceinline__ float b() const { return dof_is_prismatic<M>(d) ? b_pri : b_rev; }
+    template <int i, int j>
+    __device__ __forceinline__ float bb() const {
+        return (dof_is_prismatic<M>(i) && dof_is_prismatic<M>(j)) ? pp
+               : (dof_is_prismatic<M>(i) || dof_is_prismatic<M>(j)) ? rp : rr;
+    }
+};
+
+#ifdef CPPFLOW_SOLVE_TIMING
+// debug build only (tools/probe_solve_phases.py): cycles of lane 0 of every warp per phase of the forward / backward loops
+__device__ unsigned long long g_solve_cycles[8];
+#define PHASE_T(var) const long long var = clock64()
+#define PHASE_DECL long long ph_acc[7] = {0, 0, 0, 0, 0, 0, 0}
+#define PHASE_ADD(i, a, b) ph_acc[i] += (b) - (a)
+#define PHASE_FLUSH if (lane == 0) { for (int i_ = 0; i_ < 7; ++i_) atomicAdd(&g_solve_cycles[i_], (unsigned long long)ph_acc[i_]); }
+extern "C" int cppflow_debug_solve_cycles(unsigned long long* h_out, int reset) {
+    if (reset) { unsigned long long z[8] = {}; cudaMemcpyToSymbol(g_solve_cycles, z, sizeof(z)); return 0; }
+    cudaMemcpyFromSymbol(h_out, g_solve_cycles, sizeof(unsigned long long) * 8);
+    return 0;
+}
+#else
+#define PHASE_T(var)
+#define PHASE_DECL
+#define PHASE_ADD(i, a, b)
+#define PHASE_FLUSH
+#endif
+
+// Fused elimination (CPPFLOW_LM_FUSED): the assembly CTA of waypoint t also takes the elimination step of that waypoint,
+// so the (A_tt, b_t) block never leaves registers - what goes to the workspace is (-S_t^-1, u_t) straight away, and the
+// solve that follows only back-substitutes (HBM traffic of an iteration 1.85 -> ~1.05 GB).  The chain S_t = A_t - E
+// S_{t-1}^-1 E runs from CTA to CTA: warp w of the CTA of (path block, side, step k) waits for flags[block][side][w]
+// >= k, reads the predecessor's result block (L2: it was written a few microseconds ago by another SM), eliminates,
+// stores, and publishes k + 1.  CTAs take their (row, path block) from a ticket counter in launch order, rows in the
+// order the twisted sweep consumes them (0, T-1, 1, T-2, ..., middle), so a CTA's predecessor always holds a smaller
+// ticket and is running or done: no deadlock whatever the number of resident CTAs.
+struct FuseParams {
+    int* flags;    // [path blocks][2 sides][ABLOCK / 32 warps] steps completed, zeroed before the launch
+    int* ticket;   // CTA counter, zeroed before the launch
+    int npb;       // path blocks
+    const float* q;
+    float* x_out;  // the middle waypoint's new configuration is written here
+    SolveParams sp;
+};
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <class M, bool FUSE>
 __global__ void __launch_bounds__(ABLOCK, 2)
 lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, const float* __restrict__ target,
-                   int P, int T, const Obstacles ob, const AssembleParams prm, float* __restrict__ ws) {
+                   int P, int T, const Obstacles ob, const AssembleParams prm, float* __restrict__ ws, const FuseParams fz) {
     constexpr int D = M::NDOF;
     constexpr int NT = BlockLayout<D>::NT;
     constexpr int NW = BlockLayout<D>::NW;
@@ -107,8 +174,23 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
     fill_coll_tables<M>(tb, ob, threadIdx.x, ABLOCK);
     // grid = (path blocks, waypoints): consecutive threads take consecutive PATHS at the same waypoint t, so the
     // target pose is block-uniform and the block stores below are fully coalesced in the [t][k][path] workspace
-    const int t = blockIdx.y;
-    const int pth_raw = blockIdx.x * ABLOCK + threadIdx.x;
+    int t, pbx, f_side = 0, f_k = 0;
+    bool f_middle = false;
+    if constexpr (FUSE) {
+        __shared__ int s_ticket;
+        if (threadIdx.x == 0) s_ticket = atomicAdd(fz.ticket, 1);
+        __syncthreads();
+        const int row = s_ticket / fz.npb;  // rows in the order the twisted elimination consumes them
+        pbx = s_ticket - row * fz.npb;
+        const int m = T / 2, n1 = T - 1 - m;  // side 0 eliminates t = 0 .. m-1, side 1 t = T-1 .. m+1, then the middle
+        if (row < 2 * n1) { f_k = row >> 1; f_side = row & 1; t = f_side ? T - 1 - f_k : f_k; }
+        else if (row < T - 1) { f_k = n1; f_side = 0; t = n1; }  // m = n1 + 1: side 0's last step
+        else { f_middle = true; t = m; }
+    } else {
+        t = blockIdx.y;
+        pbx = blockIdx.x;
+    }
+    const int pth_raw = pbx * ABLOCK + threadIdx.x;
     const bool live = pth_raw < P;
     const int pth = live ? pth_raw : P - 1;  // idle lanes shadow the last path and skip the stores
     const int64_t i = (int64_t)pth * T + t;  // row of q / xv
@@ -270,26 +352,112 @@ lm_assemble_kernel(const float* __restrict__ q, const float* __restrict__ xv, co
 #pragma unroll
     for (int d = 0; d < D; ++d) A[tri(d, d)] += prm.lambda;
 
-    if (!live) return;
     // workspace layout [path / 16][t][k][path % 16] float4: the block of one 16-path group is 16 * NW contiguous floats
-    float4* out = reinterpret_cast<float4*>(ws) + ((int64_t)(pth >> 4) * T + t) * (NW / 4 * 16) + (pth & 15);
-    float blk[NW];
+    float4* grp = reinterpret_cast<float4*>(ws) + (int64_t)(pth >> 4) * T * (NW / 4 * 16) + (pth & 15);  // + t * (NW / 4 * 16)
+    auto block_at = [&](int tt) { return grp + (int64_t)tt * (NW / 4 * 16); };
+    auto store_blk = [&](int tt, const float (&S)[NT], const float (&y)[D]) {
+        float blk[NW];
 #pragma unroll
-    for (int k = 0; k < NT; ++k) blk[k] = A[k];
+        for (int k = 0; k < NT; ++k) blk[k] = S[k];
 #pragma unroll
-    for (int d = 0; d < D; ++d) blk[NT + d] = b[d];
+        for (int d = 0; d < D; ++d) blk[NT + d] = y[d];
 #pragma unroll
-    for (int k = NT + D; k < NW; ++k) blk[k] = 0.f;
+        for (int k = NT + D; k < NW; ++k) blk[k] = 0.f;
+        float4* out = block_at(tt);
 #pragma unroll
-    for (int k = 0; k < NW / 4; ++k) out[k * 16] = make_float4(blk[4 * k], blk[4 * k + 1], blk[4 * k + 2], blk[4 * k + 3]);
+        for (int k = 0; k < NW / 4; ++k) out[k * 16] = make_float4(blk[4 * k], blk[4 * k + 1], blk[4 * k + 2], blk[4 * k + 3]);
+    };
+    if constexpr (!FUSE) {
+        if (live) store_blk(t, A, b);
+    } else {
+        constexpr int NWARP = ABLOCK / 32;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const BetaSel<M> bs(fz.sp.b_rev, fz.sp.b_pri);
+        int* flags_pb = fz.flags + pbx * 2 * NWARP;
+        // lane 0 waits for the chain's predecessor, the warp follows (other SMs wrote the block: read it from L2)
+        auto wait_for = [&](const int* flag, int need) {
+            if (lane == 0) {
+                while (ld_acquire_gpu(flag) < need) __nanosleep(64);
+            }
+            __syncwarp();
+        };
+        auto load_blk = [&](int tt, float (&v)[NW]) {
+            const float4* src = block_at(tt);
+#pragma unroll
+            for (int k = 0; k < NW / 4; ++k) {
+                const float4 f = __ldcg(src + k * 16);
+                v[4 * k] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w;
+            }
+        };
+        if (!f_middle) {
+            int* flag = flags_pb + f_side * NWARP + warp;
+            float u[D];
+            if (f_k > 0) {
+                wait_for(flag, f_k);
+                float pb_[NW];
+                load_blk(f_side ? t + 1 : t - 1, pb_);
+                static_for<D>([&](auto Ii) {
+                    constexpr int i = decltype(Ii)::value;
+                    u[i] = fmaf(bs.template b<i>(), pb_[NT + i], b[i]);
+                    static_for<i + 1>([&](auto Jj) {
+                        constexpr int j = decltype(Jj)::value;
+                        A[tri(i, j)] = fmaf(bs.template bb<i, j>(), pb_[tri(i, j)], A[tri(i, j)]);
+                    });
+                });
+            } else {  // first block of a side: S = A + (beta beta^T) . 0, y = b + beta . 0 (the same fmaf, for the same bits)
+                static_for<D>([&](auto Ii) {
+                    constexpr int i = decltype(Ii)::value;
+                    u[i] = fmaf(bs.template b<i>(), 0.f, b[i]);
+                    static_for<i + 1>([&](auto Jj) {
+                        constexpr int j = decltype(Jj)::value;
+                        A[tri(i, j)] = fmaf(bs.template bb<i, j>(), 0.f, A[tri(i, j)]);
+                    });
+                });
+            }
+            sweep_neg_inverse<D>(A, u, fz.sp.pivot_floor);
+            if (live) store_blk(t, A, u);
+            __threadfence();  // this lane's stores are visible device-wide ...
+            __syncwarp();     // ... for every lane of the warp, before lane 0 publishes the step
+            if (lane == 0) st_release_gpu(flag, f_k + 1);
+        } else {
+            const int m = t, n0 = m, n1 = T - 1 - m;
+            float dx[D];
+            float L[NW], Rb[NW];
+            if (n0 > 0) { wait_for(flags_pb + warp, n0); load_blk(m - 1, L); }
+            else {
+#pragma unroll
+                for (int k = 0; k < NW; ++k) L[k] = 0.f;
+            }
+            if (n1 > 0) { wait_for(flags_pb + NWARP + warp, n1); load_blk(m + 1, Rb); }
+            else {
+#pragma unroll
+                for (int k = 0; k < NW; ++k) Rb[k] = 0.f;
+            }
+            static_for<D>([&](auto Ii) {
+                constexpr int i = decltype(Ii)::value;
+                dx[i] = fmaf(bs.template b<i>(), L[NT + i] + Rb[NT + i], b[i]);
+                static_for<i + 1>([&](auto Jj) {
+                    constexpr int j = decltype(Jj)::value;
+                    A[tri(i, j)] = fmaf(bs.template bb<i, j>(), L[tri(i, j)] + Rb[tri(i, j)], A[tri(i, j)]);
+                });
+            });
+            sweep_neg_inverse<D>(A, dx, fz.sp.pivot_floor);
+            if (live) {
+                store_blk(m, A, dx);  // the back-substitution starts from dx_m (the u slot of the middle block)
+                float xn[D];
+                load_row<D>(fz.q + i * D, xn);
+                static_for<D>([&](auto Dd) {
+                    constexpr int d = decltype(Dd)::value;
+                    xn[d] += dx[d];
+                    if (fz.sp.do_clamp) xn[d] = fminf(fmaxf(xn[d], dof_lower<M>(d)), dof_upper<M>(d));
+                });
+                float* xo = fz.x_out + i * D;
+#pragma unroll
+                for (int d = 0; d < D; ++d) xo[d] = xn[d];
+            }
+        }
+    }
 }
-
-struct SolveParams {
-    float b_rev, b_pri;  // beta of revolute / prismatic dofs
-    float pivot_floor;   // lambda: every Schur complement of J^T J + lambda I has pivots >= lambda
-    int do_clamp;
-    unsigned zero;       // always 0; a run-time value so that dependency tokens built from it survive the optimisers
-};
 
 template <int NW>
 __device__ __forceinline__ void load_block(const float* __restrict__ p, float (&v)[NW]) {
@@ -387,41 +555,6 @@ struct SolveSmem {
     }
 };
 
-// beta of dof d / product beta_i beta_j with the prismatic pattern folded at compile time (three registers instead of
-// D (D + 1) / 2 products): beta_d = b_pri for prismatic dofs, b_rev otherwise (make_params)
-template <class M>
-struct BetaSel {
-    float b_rev, b_pri, rr, rp, pp;
-    __device__ __forceinline__ BetaSel(float b_rev_, float b_pri_)
-        : b_rev(b_rev_), b_pri(b_pri_), rr(b_rev_ * b_rev_), rp(b_rev_ * b_pri_), pp(b_pri_ * b_pri_) {}
-    template <int d>
-    __device__ __forceinline__ float b() const { return dof_is_prismatic<M>(d) ? b_pri : b_rev; }
-    template <int i, int j>
-    __device__ __forceinline__ float bb() const {
-        return (dof_is_prismatic<M>(i) && dof_is_prismatic<M>(j)) ? pp
-               : (dof_is_prismatic<M>(i) || dof_is_prismatic<M>(j)) ? rp : rr;
-    }
-};
-
-#ifdef CPPFLOW_SOLVE_TIMING
-// debug build only (tools/probe_solve_phases.py): cycles of lane 0 of every warp per phase of the forward / backward loops
-__device__ unsigned long long g_solve_cycles[8];
-#define PHASE_T(var) const long long var = clock64()
-#define PHASE_DECL long long ph_acc[7] = {0, 0, 0, 0, 0, 0, 0}
-#define PHASE_ADD(i, a, b) ph_acc[i] += (b) - (a)
-#define PHASE_FLUSH if (lane == 0) { for (int i_ = 0; i_ < 7; ++i_) atomicAdd(&g_solve_cycles[i_], (unsigned long long)ph_acc[i_]); }
-extern "C" int cppflow_debug_solve_cycles(unsigned long long* h_out, int reset) {
-    if (reset) { unsigned long long z[8] = {}; cudaMemcpyToSymbol(g_solve_cycles, z, sizeof(z)); return 0; }
-    cudaMemcpyFromSymbol(h_out, g_solve_cycles, sizeof(unsigned long long) * 8);
-    return 0;
-}
-#else
-#define PHASE_T(var)
-#define PHASE_DECL
-#define PHASE_ADD(i, a, b)
-#define PHASE_FLUSH
-#endif
-
 // shared-space (32-bit) address forms of the ring primitives: the ring bookkeeping below runs once per step on the
 // critical path of a latency-bound chain, so it is kept to 32-bit adds on precomputed bases (no generic -> shared
 // conversions, no 64-bit index arithmetic, no modulo)
@@ -450,7 +583,9 @@ __device__ __forceinline__ void cp_async4_a(unsigned dst, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gmem) : "memory");
 }
 
-template <class M, int SOLVE_RING, int SOLVE_WARPS>
+// BACK_ONLY: the elimination and the middle block were done by the fused assembly (lm_assemble_kernel<M, true>): the
+// workspace already holds (-S_t^-1, u_t) and, in the middle block's u slot, dx_m; only the back-substitution runs.
+template <class M, int SOLVE_RING, int SOLVE_WARPS, bool BACK_ONLY = false>
 __global__ void __launch_bounds__(32 * SOLVE_WARPS, 512 / (32 * SOLVE_WARPS))
 lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T64, const SolveParams prm, float* __restrict__ ws,
                       float* __restrict__ x_out) {
@@ -566,6 +701,7 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T64, const
     for (int d = 0; d < D; ++d) u[d] = 0.f;
 
     // ---- elimination sweep (steps s = 0 .. n_iter-1):  S_t = A_t + (beta beta^T) . nS,  y_t = b_t + beta . u_in
+    if constexpr (!BACK_ONLY) {
 #pragma unroll
     for (int j = 0; j < SOLVE_RING; ++j)
         if (j < n_iter) issue(j, j < n0 ? j : -1, j < n1 ? T - 1 - j : -1, 0u);
@@ -620,6 +756,7 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T64, const
         PHASE_ADD(3, c3, c4);
         advance();
     }
+    }  // !BACK_ONLY
     PHASE_T(cf0);
     __threadfence();                                  // the generic stores above are performed ...
     asm volatile("fence.proxy.async;" ::: "memory");  // ... and ordered before the async-proxy (TMA) reads below
@@ -657,7 +794,17 @@ lm_block_solve_kernel(const float* __restrict__ q, int64_t P, int64_t T64, const
 
     // ---- middle block: S_m = A_m + (beta beta^T) . (nS_left + nS_right),  y_m = b_m + beta . (u_left + u_right)
     float dx[D];
-    {
+    if constexpr (BACK_ONLY) {
+        const float4* src = reinterpret_cast<const float4*>(wsg + m * SM::BLK_BYTES) + l;
+        float tail[NW - NT / 4 * 4];  // the float4s that hold the u slot (dx_m)
+#pragma unroll
+        for (int k = NT / 4; k < NV; ++k) {
+            const float4 f = src[k * 16];
+            tail[4 * (k - NT / 4)] = f.x; tail[4 * (k - NT / 4) + 1] = f.y; tail[4 * (k - NT / 4) + 2] = f.z; tail[4 * (k - NT / 4) + 3] = f.w;
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) dx[i] = tail[NT - NT / 4 * 4 + i];
+    } else {
         float Sm[NT];
         float blk[NW];
         const float4* src = reinterpret_cast<const float4*>(wsg + m * SM::BLK_BYTES) + l;
@@ -1119,17 +1266,17 @@ static int launch_assemble(const cppflow_lm_params* p, const float* q, const flo
     static const char* pad_kb = std::getenv("CPPFLOW_ASM_SMEM_PAD_KB");
     if (pad_kb) sh += (size_t)std::atoi(pad_kb) * 1024;
     static SmemGrant granted;  // per template instantiation and device
-    if (int rc = ensure_dynamic_smem(lm_assemble_kernel<M>, sh, granted)) return rc;
+    if (int rc = ensure_dynamic_smem(lm_assemble_kernel<M, false>, sh, granted)) return rc;
     const dim3 grid(grid_for(P, ABLOCK), (unsigned)T);
-    lm_assemble_kernel<M><<<grid, ABLOCK, sh, st>>>(q, xv, target, (int)P, (int)T, ob, ap, ws);
+    lm_assemble_kernel<M, false><<<grid, ABLOCK, sh, st>>>(q, xv, target, (int)P, (int)T, ob, ap, ws, FuseParams{});
     return CPPFLOW_OK;
 }
 
-template <class M, int RING, int WARPS = SOLVE_WARPS_DEFAULT>
+template <class M, int RING, int WARPS = SOLVE_WARPS_DEFAULT, bool BACK_ONLY = false>
 static int launch_solve_variant(const SolveParams& sp, const float* q, int64_t P, int64_t T, bool high_priority,
                                 float* ws, float* x_out, cudaStream_t st) {
     const size_t sh = SolveSmem<M::NDOF, RING>::BYTES * WARPS;
-    auto kern = lm_block_solve_kernel<M, RING, WARPS>;
+    auto kern = lm_block_solve_kernel<M, RING, WARPS, BACK_ONLY>;
     static SmemGrant granted;  // per template instantiation and device
     if (int rc = ensure_dynamic_smem(kern, sh, granted)) return rc;
     int prio_high = 0;
@@ -1215,8 +1362,43 @@ static int launch_solve(const cppflow_lm_params* p, const float* q, int64_t P, i
 }
 
 template <class M>
+static size_t ws_block_bytes(int64_t P, int64_t T) {
+    return ((size_t)((P + 15) / 16 * 16) * (size_t)T * BlockLayout<M::NDOF>::NW * sizeof(float) + 255) / 256 * 256;
+}
+// flags + ticket of the fused elimination, behind the blocks
+static size_t ws_tail_bytes(int64_t P) {
+    return ((size_t)grid_for(P, ABLOCK) * 2 * (ABLOCK / 32) + 64) * sizeof(int);
+}
+template <class M>
 static size_t ws_bytes(int64_t P, int64_t T) {
-    return (size_t)((P + 15) / 16 * 16) * (size_t)T * BlockLayout<M::NDOF>::NW * sizeof(float);
+    return ws_block_bytes<M>(P, T) + ws_tail_bytes(P);
+}
+
+// CPPFLOW_LM_FUSED: assembly + elimination in one kernel (FuseParams above), then the back-substitution
+template <class M>
+static int launch_fused_step(const cppflow_lm_params* p, const float* q, const float* xv, const float* target, int64_t P,
+                             int64_t T, const Obstacles& ob, int flags, float* ws, float* x_out, cudaStream_t st) {
+    AssembleParams ap;
+    SolveParams sp;
+    make_params<M>(p, ob.n, flags & CPPFLOW_LM_CLAMP, ap, sp);
+    ap.prefetch = 0;  // rows are not taken in waypoint order
+    const size_t sh = sizeof(float) * ABLOCK * SmemLayout<M>::N_FULL;
+    static SmemGrant granted;  // per template instantiation and device
+    if (int rc = ensure_dynamic_smem(lm_assemble_kernel<M, true>, sh, granted)) return rc;
+    FuseParams fz;
+    int* tail = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ws) + ws_block_bytes<M>(P, T));
+    fz.npb = (int)grid_for(P, ABLOCK);
+    fz.flags = tail + 64;
+    fz.ticket = tail;
+    fz.q = q;
+    fz.x_out = x_out;
+    fz.sp = sp;
+    cudaError_t e = cudaMemsetAsync(tail, 0, ws_tail_bytes(P), st);
+    if (e != cudaSuccess) return fail(CPPFLOW_E_CUDA, "lm_full fused: memset: %s", cudaGetErrorString(e));
+    lm_assemble_kernel<M, true><<<dim3((unsigned)(fz.npb * T)), ABLOCK, sh, st>>>(q, xv, target, (int)P, (int)T, ob, ap, ws, fz);
+    if (T < 2) return CPPFLOW_OK;  // a single waypoint is the middle block: nothing to back-substitute
+    if (flags & CPPFLOW_LM_OVERLAP) return launch_solve_variant<M, SOLVE_RING_OVERLAP, SOLVE_WARPS_DEFAULT, true>(sp, q, P, T, true, ws, x_out, st);
+    return launch_solve_variant<M, SOLVE_RING_ALONE, SOLVE_WARPS_DEFAULT, true>(sp, q, P, T, false, ws, x_out, st);
 }
 
 }  // namespace cppflow
@@ -1284,6 +1466,21 @@ extern "C" int cppflow_lm_full_step(int robot, const cppflow_lm_params* params, 
                                     const float* d_target, int64_t P, int64_t T, const float* h_cuboids,
                                     const float* h_Tcuboids, int n_obstacles, int do_clamp, void* d_workspace,
                                     size_t workspace_bytes, float* d_x_out, void* stream) {
+    if (do_clamp & CPPFLOW_LM_FUSED) {
+        if (P == 0 || T == 0) return CPPFLOW_OK;
+        if (int rc = check_common(robot, params, P, T, d_workspace, workspace_bytes)) return rc;
+        CPPFLOW_CHECK_ARG(d_q && d_x_out, "null pointer");
+        CPPFLOW_CHECK_ARG(!params->use_pose || d_target, "target path required when use_pose");
+        CPPFLOW_CHECK_ARG(P * T < ((int64_t)1 << 31) / 2, "P * T too large for the fused elimination's ticket counter");
+        Obstacles ob;
+        if (int rc = make_obstacles(h_cuboids, h_Tcuboids, n_obstacles, ob)) return rc;
+        int rc = CPPFLOW_OK;
+        CPPFLOW_DISPATCH_ROBOT(robot, rc = launch_fused_step<M>(params, d_q, d_xv, d_target, P, T, ob, do_clamp, (float*)d_workspace,
+                                                                d_x_out, (cudaStream_t)stream));
+        if (rc) return rc;
+        CPPFLOW_CHECK_LAUNCH();
+        return CPPFLOW_OK;
+    }
     if (int rc = cppflow_lm_full_assemble(robot, params, d_q, d_xv, d_target, P, T, h_cuboids, h_Tcuboids, n_obstacles,
                                           d_workspace, workspace_bytes, stream))
         return rc;

@@ -30,7 +30,7 @@ def _on_device(fn):
 
 
 ROBOT_IDS = {"fetch": 0, "fetch_arm": 1, "panda": 2}
-LM_CLAMP, LM_OVERLAP = 1, 2  # CPPFLOW_LM_CLAMP / CPPFLOW_LM_OVERLAP (include/cppflow_b200.h)
+LM_CLAMP, LM_OVERLAP, LM_FUSED = 1, 2, 4  # CPPFLOW_LM_CLAMP / _OVERLAP / _FUSED (include/cppflow_b200.h)
 
 
 def _info(robot_id: int) -> _lib.RobotInfoC:
@@ -235,8 +235,9 @@ def _workspace(device, nbytes: int, key: str) -> torch.Tensor:
 def lm_full_step(rid: int, ndof: int, params: LmParamsC, q: torch.Tensor, xv: Optional[torch.Tensor],
                  target: Optional[torch.Tensor], P: int, T: int, ob: Optional[Obstacles], clamp: bool,
                  out: Optional[torch.Tensor] = None, overlap: bool = False,
-                 workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """levenberg_marquardt_full (+ clamp) for P paths of T waypoints on the current stream.  `overlap`: launch the
+                 workspace: Optional[torch.Tensor] = None, fused: bool = False) -> torch.Tensor:
+    """levenberg_marquardt_full (+ clamp) for P paths of T waypoints on the current stream.  `fused`: CPPFLOW_LM_FUSED
+    (elimination inside the assembly kernel, same bits).  `overlap`: launch the
     solve with CPPFLOW_LM_OVERLAP (footprint that fits next to an assembly CTA, high launch priority) - for callers that run several chunks
     of paths on several streams (pipeline.ResidentPipeline), which must also pass one `workspace` per stream."""
     q = _check_q(q, ndof)
@@ -256,7 +257,7 @@ def lm_full_step(rid: int, ndof: int, params: LmParamsC, q: torch.Tensor, xv: Op
         assert ws.is_cuda and ws.dtype == torch.uint8 and ws.numel() >= nbytes, "workspace too small"
     x_out = torch.empty_like(q) if out is None else out
     cu, tc, no = _obs(ob)
-    flags = (LM_CLAMP if clamp else 0) | (LM_OVERLAP if overlap else 0)
+    flags = (LM_CLAMP if clamp else 0) | (LM_OVERLAP if overlap else 0) | (LM_FUSED if fused else 0)
     check(lib.cppflow_lm_full_step(rid, params, ptr(q), ptr(xv), ptr(target), P, T, cu, tc, no, flags, ptr(ws),
                                    ws.numel(), ptr(x_out), stream_ptr(q.device)))
     return x_out

@@ -160,6 +160,10 @@ int cppflow_lm_full_solve(int robot, const cppflow_lm_params* params, const floa
  * assembly of another chunk of paths enqueued on another stream (same results bit for bit). */
 #define CPPFLOW_LM_CLAMP 1
 #define CPPFLOW_LM_OVERLAP 2
+/* cppflow_lm_full_step only: the assembly CTA of a waypoint also takes the elimination step of that waypoint (the chain
+ * runs from CTA to CTA through L2), so the (A, b) blocks never reach HBM; the solve then only back-substitutes.  Same
+ * results bit for bit. */
+#define CPPFLOW_LM_FUSED 4
 
 /* run_lm_alternating_loss for ONE path (optimization.py:147-373; called by run_lm_optimization :376-426 with
  * ALT_LOSS_V2_1_DIFF / ALT_LOSS_V2_1_POSE): pose-only steps until the position and rotation errors are inside the

@@ -44,8 +44,10 @@ def test_error_codes_without_gpu():
     info = _lib.RobotInfoC()
     assert lib.cppflow_robot_info_get(7, info) == -1  # CPPFLOW_E_INVALID
     assert b"unknown robot id" in lib.cppflow_last_error()
-    assert lib.cppflow_lm_full_workspace_bytes(0, 8192, 300) == 8192 * 300 * 44 * 4
-    assert lib.cppflow_lm_full_workspace_bytes(2, 10, 20) == 16 * 20 * 36 * 4  # paths padded to 16-path groups
+    # blocks (paths padded to 16-path groups, rounded to 256 bytes) + the flags / ticket of the fused elimination:
+    # (path blocks of 256) x 2 sides x 8 warps + 64 ints
+    assert lib.cppflow_lm_full_workspace_bytes(0, 8192, 300) == 8192 * 300 * 44 * 4 + (32 * 2 * 8 + 64) * 4
+    assert lib.cppflow_lm_full_workspace_bytes(2, 10, 20) == 16 * 20 * 36 * 4 + (1 * 2 * 8 + 64) * 4
     assert lib.cppflow_dp_search_workspace_bytes(175, 295) >= 4 * (295 * 175 + 294 * 175 * 175)
     with pytest.raises(_lib.CppflowError):
         _lib.check(-1)

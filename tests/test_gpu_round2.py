@@ -517,3 +517,30 @@ def test_resident_pipeline_graph_replay_equals_eager(robots):
         torch.cuda.synchronize()
         assert torch.equal(out_e, ref) and torch.equal(out_g, ref)
         assert torch.equal(metrics, m_eager)
+
+
+@pytest.mark.parametrize("r", ROBOTS)
+def test_fused_elimination_equals_two_kernel_step(robots, r):
+    """CPPFLOW_LM_FUSED: the assembly CTAs take the elimination steps (chain handed from CTA to CTA through L2), the solve
+    only back-substitutes.  Same bits as assembly + solve, for every path / waypoint count (one waypoint = only the middle
+    block, even / odd T, ragged path counts, more CTAs than can be resident at once) and parameter set."""
+    from cppflow_b200 import ops
+    from cppflow_b200.lm_hyper_parameters import all_terms_parameters, ALT_LOSS_V2_1_DIFF
+
+    rob = robots[r]
+    cuboids, Tcuboids = cuboid_tensors(OBSTACLES[r])
+    ob = ops.Obstacles(cuboids, Tcuboids)
+    for P, T in ((1, 1), (3, 2), (5, 3), (17, 4), (33, 5), (300, 9), (1000, 64), (2100, 301), (257, 295)):
+        m, target, x0 = synthetic_problem(r, P, T, seed=P + T)
+        x, tg = x0.to(DEV), target.to(DEV)
+        for name, pm in (("all", all_terms_parameters()), ("diff", ALT_LOSS_V2_1_DIFF)):
+            if pm.use_virtual_configs and 2 * pm.n_virtual_configs >= T:
+                continue
+            prm = ops.make_params(pm)
+            xv = x.clone() if pm.use_virtual_configs else None
+            ref = ops.lm_full_step(rob.robot_id, rob.ndof, prm, x, xv, tg, P, T, ob, True)
+            got = ops.lm_full_step(rob.robot_id, rob.ndof, prm, x, xv, tg, P, T, ob, True, fused=True)
+            assert torch.equal(got, ref), (r, P, T, name, float((got - ref).abs().max()))
+            got2 = ops.lm_full_step(rob.robot_id, rob.ndof, prm, x, xv, tg, P, T, ob, False, fused=True, overlap=True)
+            ref2 = ops.lm_full_step(rob.robot_id, rob.ndof, prm, x, xv, tg, P, T, ob, False)
+            assert torch.equal(got2, ref2), (r, P, T, name, "no clamp / overlap variant")
