@@ -1332,25 +1332,10 @@ static int launch_solve(const cppflow_lm_params* p, const float* q, int64_t P, i
         lm_block_solve_resident_kernel<M><<<(unsigned)P, 32, sh, st>>>(q, P, T, sp, ws, x_out);
         return CPPFLOW_OK;
     }
-    // experiment switch (profiles/r02_notes.md): CPPFLOW_SOLVE = "tma" (ring kernel), "tma8r3" (8 warps, 3-slot ring: a
-    // whole-SM CTA), "v2w1" / "v2w2" / "v2w4" / "v2w8" (register-resident kernel, warps per CTA), suffix "np" = no prefetch
+    // CPPFLOW_SOLVE = "tma" keeps the ring kernel for every path count (A/B of the two kernels, tools/probe_solve.py);
+    // the other variants measured in round 2 (8 or 1 warps per CTA, the register-resident kernel with 2 / 4 / 8 warps or
+    // without prefetch) are in profiles/r02_notes.md
     static const char* which = std::getenv("CPPFLOW_SOLVE");
-    if (which && std::strncmp(which, "v2", 2) == 0) {
-        const bool np = std::strstr(which, "np") != nullptr;
-        const bool hp = (flags & CPPFLOW_LM_OVERLAP) != 0;
-        const int w = std::strstr(which, "w8") ? 8 : std::strstr(which, "w2") ? 2 : std::strstr(which, "w1") ? 1 : 4;
-        if (np) return w == 8 ? launch_solve_v2<M, 8, false>(sp, q, P, T, hp, ws, x_out, st) : launch_solve_v2<M, 4, false>(sp, q, P, T, hp, ws, x_out, st);
-        switch (w) {
-            case 1: return launch_solve_v2<M, 1, true>(sp, q, P, T, hp, ws, x_out, st);
-            case 2: return launch_solve_v2<M, 2, true>(sp, q, P, T, hp, ws, x_out, st);
-            case 8: return launch_solve_v2<M, 8, true>(sp, q, P, T, hp, ws, x_out, st);
-            default: return launch_solve_v2<M, 4, true>(sp, q, P, T, hp, ws, x_out, st);
-        }
-    }
-    if (which && std::strcmp(which, "tma8r3") == 0)
-        return launch_solve_variant<M, 3, 8>(sp, q, P, T, (flags & CPPFLOW_LM_OVERLAP) != 0, ws, x_out, st);
-    if (which && std::strcmp(which, "tma1") == 0)
-        return launch_solve_variant<M, 4, 1>(sp, q, P, T, (flags & CPPFLOW_LM_OVERLAP) != 0, ws, x_out, st);
     // few paths: the chain latency is all there is, and the register-resident kernel's step is the shortest (no ring
     // bookkeeping): P = 512 alone 0.128 ms against 0.21; under overlap it only wins for chunks of <= 256 paths
     // (4 chunks of 256: 0.203 ms per iteration against 0.254, of 512: 0.337 against 0.286).  Bit-identical either way.
