@@ -141,6 +141,7 @@ _PROTOTYPES = {
     "cppflow_path_metrics_ex": (_I, [_I, _VP, _VP, _I64, _I64, c_float_p, c_float_p, _I, _I, _VP, _VP]),
     "cppflow_sm_partition_create": (_I, [_I, _I, _I, _I, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_I), C.POINTER(_I)]),
     "cppflow_fp32_probe": (_I, [_I, _I, _VP, C.POINTER(C.c_double), _VP]),
+    "cppflow_neighbour_probe": (_I, [_I, _I, _I, _I, _VP, _VP]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
 

@@ -272,6 +272,9 @@ int cppflow_sm_partition_create(int device, int min_sms_first, int n_streams_fir
 /* Measurement aid (no reference counterpart): dependent-free FP32 FMA loop on `blocks` x 1024 threads, used by
  * bench.py to measure the FP32 roofline denominator on the box.  *flops_out = FLOPs of the launch. */
 int cppflow_fp32_probe(int blocks, int iters, float* d_scratch, double* flops_out, void* stream);
+/* Measurement aid (no reference counterpart): a stand-in neighbour kernel for co-residency experiments - 256-thread CTAs
+ * of FMA chains holding `smem_bytes` of shared memory, untouched (touch = 0) or accessed `touch` times per iteration. */
+int cppflow_neighbour_probe(int blocks, int iters, int smem_bytes, int touch, float* d_scratch, void* stream);
 
 #ifdef __cplusplus
 }
