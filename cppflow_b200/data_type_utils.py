@@ -109,18 +109,82 @@ def get_obstacles(problem_dict: Dict, device=None):
     return obstacles, Tcuboids, cuboids
 
 
+def problem_dict_from_yaml(filepath: str) -> Dict:
+    """Normalise one problem yaml (the reference's format, problems/*.yaml: `obstacles` is a list of lists of
+    single-key maps) into the dict layout of data/problems.json."""
+    import yaml
+
+    with open(filepath) as f:
+        d = yaml.load(f, Loader=yaml.FullLoader)
+    for key in ("robot", "path_name", "path_offset_frame", "path_xyz_offset", "path_R_offset"):
+        assert key in d, f"problem file '{filepath}' has no '{key}'"
+    obstacles = []
+    for obs in d.get("obstacles", []) or []:
+        parsed = {}
+        for item in ([obs] if isinstance(obs, dict) else obs):
+            parsed.update(item)
+        obstacles.append({k: float(v) for k, v in parsed.items()})
+    out = {
+        "robot": d["robot"],
+        "path_name": d["path_name"],
+        "path_offset_frame": d["path_offset_frame"],
+        "path_xyz_offset": [float(v) for v in d["path_xyz_offset"]],
+        "path_R_offset": [[float(v) for v in row] for row in d["path_R_offset"]],
+        "obstacle_xyz_offset": [float(v) for v in d.get("obstacle_xyz_offset", [0, 0, 0])],
+        "source": filepath,
+    }
+    if "obstacles" in d:
+        out["obstacles"] = obstacles
+    return out
+
+
+def target_path_from_csv(filepath: str) -> np.ndarray:
+    """A path csv of the reference (paths/*.csv: header row, then time,x,y,z,qw,qx,qy,qz) -> float64 [T, 7]."""
+    import csv
+
+    with open(filepath) as f:
+        rows = [[float(x) for x in row] for i, row in enumerate(csv.reader(f, delimiter=",")) if i > 0 and row]
+    path = np.array(rows, dtype=np.float64)
+    assert path.ndim == 2 and path.shape[1] == 8, f"'{filepath}': expected 8 columns (time, xyz, wxyz), got {path.shape}"
+    return path[:, 1:]
+
+
+def _named_target_path(path_name: str, search_from: Optional[str]) -> np.ndarray:
+    """The packed path of that name, else `<path_name>.csv` beside the problem file, in its `paths/`, or in `../paths/`
+    (the reference keeps problems/ and paths/ as siblings)."""
+    paths = _paths()
+    if path_name in paths:
+        return paths[path_name]
+    tried = []
+    if search_from is not None:
+        here = os.path.dirname(os.path.abspath(search_from))
+        for folder in (here, os.path.join(here, "paths"), os.path.join(here, os.pardir, "paths")):
+            candidate = os.path.join(folder, path_name + ".csv")
+            tried.append(candidate)
+            if os.path.isfile(candidate):
+                return target_path_from_csv(candidate)
+    raise FileNotFoundError(f"no target path '{path_name}': not a packed path {sorted(paths.keys())} and not at {tried}")
+
+
 def problem_from_filename(constraints: Optional[Constraints], problem_filename: str, filepath_override: Optional[str] = None,
                           robot: Optional[Robot] = None, device=None) -> Problem:
-    """Build a Problem (target path on `device`) from one of the packed problem definitions."""
-    assert "yaml" not in problem_filename, "problem_filename should not include the .yaml file extension"
-    assert filepath_override is None, "only the packed problem definitions are available (data/problems.json)"
+    """data_type_utils.py:148-219.  Build a Problem (target path on `device`) from one of the packed problem
+    definitions, or, with `filepath_override`, from a problem yaml in the reference's format (its target path is a
+    packed path or a csv next to the yaml).  As in the reference (:184), a caller-provided robot excludes obstacles."""
     device = config.DEVICE if device is None else device
-    d = _problems()[problem_filename]
+    if filepath_override is None:
+        assert "yaml" not in problem_filename, "problem_filename should not include the .yaml file extension"
+        assert problem_filename in _problems(), f"unknown problem '{problem_filename}' (known: {sorted(_problems())})"
+        d = _problems()[problem_filename]
+    else:
+        d = problem_dict_from_yaml(filepath_override)
     if robot is None:
         robot = get_robot(d["robot"])
+    elif filepath_override is not None:
+        assert "obstacles" not in d, f"Error - obstacles found for {problem_filename} but robot is provided"
     obstacles, Tcuboids, cuboids = get_obstacles(d, device=device)
-    target_path = offset_target_path(_paths()[d["path_name"]], d["path_offset_frame"], d["path_xyz_offset"],
-                                     d["path_R_offset"]).to(device)
+    target_path = offset_target_path(_named_target_path(d["path_name"], filepath_override), d["path_offset_frame"],
+                                     d["path_xyz_offset"], d["path_R_offset"]).to(device)
     return Problem(constraints if constraints is not None else DEFAULT_CONSTRAINTS, target_path, None, robot,
                    d["path_name"], problem_filename, obstacles, Tcuboids, cuboids, [])
 

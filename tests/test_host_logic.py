@@ -109,6 +109,45 @@ def test_problem_loader_matches_reference_files():
         Problem(DEFAULT_CONSTRAINTS, torch.zeros((4, 7)), None, _FakeRobot(), "bad", "bad", [], [], [], [])
 
 
+def test_problem_from_user_yaml_and_csv(tmp_path):
+    """data_type_utils.py:167-173 (`filepath_override`, the route tests/planners_test.py:96 takes): a problem yaml in
+    the reference's layout gives the same Problem as the packed definition; a path csv beside the yaml is picked up."""
+    from cppflow_b200.data_type_utils import _problems, problem_from_filename
+
+    d = _problems()["fetch__s"]
+    lines = [f"robot: {d['robot']}", f"path_name: {d['path_name']}", f"path_offset_frame: {d['path_offset_frame']}",
+             f"path_xyz_offset: {d['path_xyz_offset']}", "path_R_offset:"]
+    lines += [f"  - {row}" for row in d["path_R_offset"]]
+    lines += [f"obstacle_xyz_offset: {d['obstacle_xyz_offset']}", "obstacles:"]
+    for obs in d["obstacles"]:
+        items = list(obs.items())
+        lines.append(f"  - - {items[0][0]}: {items[0][1]}")
+        lines += [f"    - {k}: {v}" for k, v in items[1:]]
+    yaml_path = tmp_path / "my_problem.yaml"
+    yaml_path.write_text("\n".join(lines) + "\n")
+    packed = problem_from_filename(None, "fetch__s", device="cpu")
+    loaded = problem_from_filename(None, "", filepath_override=str(yaml_path), device="cpu")
+    assert torch.equal(packed.target_path, loaded.target_path) and loaded.robot.name == packed.robot.name
+    assert len(loaded.obstacles_cuboids) == len(packed.obstacles_cuboids) > 0
+    for a, b in zip(packed.obstacles_cuboids + packed.obstacles_Tcuboids, loaded.obstacles_cuboids + loaded.obstacles_Tcuboids):
+        assert torch.equal(a, b)
+    with pytest.raises(AssertionError):  # :184 - a caller-provided robot excludes obstacles
+        problem_from_filename(None, "", filepath_override=str(yaml_path), robot=packed.robot, device="cpu")
+
+    # a user path: csv beside the yaml, header + time,x,y,z,qw,qx,qy,qz
+    rows = ["time,x,y,z,qw,qx,qy,qz"] + [f"{0.1 * i},{0.01 * i},0.2,0.3,1.0,0.0,0.0,0.0" for i in range(5)]
+    (tmp_path / "my_line.csv").write_text("\n".join(rows) + "\n")
+    (tmp_path / "line.yaml").write_text(
+        "robot: panda\npath_name: my_line\npath_offset_frame: world\npath_xyz_offset: [0.4, 0.0, 0.1]\n"
+        "path_R_offset:\n  - [1, 0, 0]\n  - [0, 1, 0]\n  - [0, 0, 1]\n")
+    p = problem_from_filename(None, "", filepath_override=str(tmp_path / "line.yaml"), device="cpu")
+    assert p.n_timesteps == 5 and p.obstacle_tables.n == 0 and p.robot.name == "panda"
+    np.testing.assert_allclose(p.target_path[4].numpy(), [0.44, 0.2, 0.4, 1, 0, 0, 0], atol=1e-6)
+    (tmp_path / "missing.yaml").write_text((tmp_path / "line.yaml").read_text().replace("my_line", "nowhere"))
+    with pytest.raises(FileNotFoundError):
+        problem_from_filename(None, "", filepath_override=str(tmp_path / "missing.yaml"), device="cpu")
+
+
 def test_shard_range_and_costs():
     from cppflow_b200.distributed import shard_range, path_costs, path_keys, decode_key, INVALID_COST
 
