@@ -104,7 +104,7 @@ class LmLoopJobC(C.Structure):
     ]
 
 
-ABI_VERSION = 3  # CPPFLOW_ABI_VERSION of include/cppflow_b200.h
+ABI_VERSION = 4  # CPPFLOW_ABI_VERSION of include/cppflow_b200.h
 
 _VP, _I, _I64, _SZ, _F, _DBL = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float, C.c_double
 _PROTOTYPES = {
@@ -123,6 +123,7 @@ _PROTOTYPES = {
     "cppflow_env_collision_distances": (_I, [_I, _VP, _I64, c_float_p, c_float_p, _VP, _VP, _VP]),
     "cppflow_collision_flags": (_I, [_I, _VP, _I64, c_float_p, c_float_p, _I, _VP, _VP, _VP]),
     "cppflow_lm_full_workspace_bytes": (_SZ, [_I, _I64, _I64]),
+    "cppflow_lm_full_workspace_bytes_ex": (_SZ, [_I, _I64, _I64, _I]),
     "cppflow_lm_full_step": (_I, [_I, C.POINTER(LmParamsC), _VP, _VP, _VP, _I64, _I64, c_float_p, c_float_p, _I, _I,
                                   _VP, _SZ, _VP, _VP]),
     "cppflow_lm_full_assemble": (_I, [_I, C.POINTER(LmParamsC), _VP, _VP, _VP, _I64, _I64, c_float_p, c_float_p, _I, _VP,

@@ -1219,6 +1219,10 @@ lm_block_solve_v2_kernel(const float* __restrict__ q, int64_t P, int64_t T, cons
     }
 }
 
+}  // namespace cppflow
+#include "lm_segsolve.cuh"
+namespace cppflow {
+
 constexpr int64_t SOLVE_V2_MAX_PATHS_ALONE = 1024, SOLVE_V2_MAX_PATHS_OVERLAP = 256;  // see launch_solve
 constexpr int64_t SOLVE_RESIDENT_MAX_PATHS = 8;  // beyond a handful of paths the streaming kernel's throughput wins
 
@@ -1320,11 +1324,66 @@ static int launch_solve_v2(const SolveParams& sp, const float* q, int64_t P, int
 }
 
 template <class M>
+static size_t ws_block_bytes(int64_t P, int64_t T) {
+    return ((size_t)((P + 15) / 16 * 16) * (size_t)T * BlockLayout<M::NDOF>::NW * sizeof(float) + 255) / 256 * 256;
+}
+// flags + ticket of the fused elimination, behind the blocks
+static size_t ws_tail_bytes(int64_t P) {
+    return ((size_t)grid_for(P, ABLOCK) * 2 * (ABLOCK / 32) + 64) * sizeof(int);
+}
+// segments of the segmented solve asked for by the flags (0 = the twisted solve): at least 4 waypoints per segment
+static int seg_count(int64_t T, int flags) {
+    int64_t n = (flags >> CPPFLOW_LM_SEGMENTS_SHIFT) & 0xff;
+    if (n > SEG_MAX_SEGMENTS) n = SEG_MAX_SEGMENTS;
+    const int64_t s = n < T / 4 ? n : T / 4;
+    return s >= 2 ? (int)s : 0;
+}
+template <class M>
+static size_t ws_seg_corner_bytes(int64_t P, int S) {
+    return (size_t)((P + 15) / 16) * S * 2 * SegLayout<M::NDOF>::corner_f4() * 16;
+}
+template <class M>
+static size_t ws_seg_x_bytes(int64_t P, int S) {
+    return ((size_t)((P + 15) / 16) * (S - 1) * SegLayout<M::NDOF>::x_f4() * 16 + 255) / 256 * 256;
+}
+// [blocks][flags + ticket of the fused elimination][segmented solve: factors | corners | separator solutions]
+template <class M>
+static size_t ws_bytes(int64_t P, int64_t T, int flags = 0) {
+    const size_t n = ws_block_bytes<M>(P, T) + ws_tail_bytes(P);
+    const int S = (flags & CPPFLOW_LM_FUSED) ? 0 : seg_count(T, flags);
+    if (S == 0) return n;
+    return (n + 255) / 256 * 256 + ws_block_bytes<M>(P, T) + ws_seg_corner_bytes<M>(P, S) + ws_seg_x_bytes<M>(P, S);
+}
+
+template <class M>
+static int launch_solve_segmented(const SolveParams& sp, const float* q, int64_t P, int64_t T, int S, float* ws,
+                                  float* x_out, cudaStream_t st) {
+    unsigned char* base = reinterpret_cast<unsigned char*>(ws);
+    size_t off = (ws_block_bytes<M>(P, T) + ws_tail_bytes(P) + 255) / 256 * 256;
+    float* fac = reinterpret_cast<float*>(base + off);
+    off += ws_block_bytes<M>(P, T);
+    float* corners = reinterpret_cast<float*>(base + off);
+    off += ws_seg_corner_bytes<M>(P, S);
+    float* sepx = reinterpret_cast<float*>(base + off);
+    const SegGeom geo{(int)T, S};
+    const int64_t warps = (P + 15) / 16 * S;
+    constexpr int W = 1;  // single-warp CTAs spread the chains over the SMs' schedulers (as the register-resident solve)
+    lm_seg_eliminate_kernel<M, W><<<grid_for(warps, W), 32 * W, 0, st>>>(P, geo, sp, ws, fac, corners);
+    const size_t sh = (size_t)(S - 1) * seg_node_floats<M::NDOF>() * sizeof(float);
+    static SmemGrant granted;  // per template instantiation and device
+    if (int rc = ensure_dynamic_smem(lm_seg_reduced_kernel<M>, (size_t)(SEG_MAX_SEGMENTS - 1) * seg_node_floats<M::NDOF>() * sizeof(float), granted)) return rc;
+    lm_seg_reduced_kernel<M><<<grid_for(P, 16), 32 * SEG_REDUCED_WARPS, sh, st>>>(q, P, geo, sp, ws, corners, sepx, x_out);
+    lm_seg_substitute_kernel<M, W><<<grid_for(warps, W), 32 * W, 0, st>>>(q, P, geo, sp, ws, fac, sepx, x_out);
+    return CPPFLOW_OK;
+}
+
+template <class M>
 static int launch_solve(const cppflow_lm_params* p, const float* q, int64_t P, int64_t T, int flags, float* ws,
                         float* x_out, cudaStream_t st) {
     AssembleParams ap;
     SolveParams sp;
     make_params<M>(p, 0, flags & CPPFLOW_LM_CLAMP, ap, sp);
+    if (const int S = seg_count(T, flags)) return launch_solve_segmented<M>(sp, q, P, T, S, ws, x_out, st);
     if (P <= SOLVE_RESIDENT_MAX_PATHS && solve_resident_smem<M>(T) <= 200 * 1024) {
         const size_t sh = solve_resident_smem<M>(T);
         static SmemGrant granted;  // per template instantiation and device
@@ -1344,19 +1403,6 @@ static int launch_solve(const cppflow_lm_params* p, const float* q, int64_t P, i
         return launch_solve_v2<M, 1, true>(sp, q, P, T, overlap, ws, x_out, st);
     if (overlap) return launch_solve_variant<M, SOLVE_RING_OVERLAP>(sp, q, P, T, true, ws, x_out, st);
     return launch_solve_variant<M, SOLVE_RING_ALONE>(sp, q, P, T, false, ws, x_out, st);
-}
-
-template <class M>
-static size_t ws_block_bytes(int64_t P, int64_t T) {
-    return ((size_t)((P + 15) / 16 * 16) * (size_t)T * BlockLayout<M::NDOF>::NW * sizeof(float) + 255) / 256 * 256;
-}
-// flags + ticket of the fused elimination, behind the blocks
-static size_t ws_tail_bytes(int64_t P) {
-    return ((size_t)grid_for(P, ABLOCK) * 2 * (ABLOCK / 32) + 64) * sizeof(int);
-}
-template <class M>
-static size_t ws_bytes(int64_t P, int64_t T) {
-    return ws_block_bytes<M>(P, T) + ws_tail_bytes(P);
 }
 
 // CPPFLOW_LM_FUSED: assembly + elimination in one kernel (FuseParams above), then the back-substitution
@@ -1390,18 +1436,22 @@ static int launch_fused_step(const cppflow_lm_params* p, const float* q, const f
 
 using namespace cppflow;
 
-extern "C" size_t cppflow_lm_full_workspace_bytes(int robot, int64_t P, int64_t T) {
+extern "C" size_t cppflow_lm_full_workspace_bytes_ex(int robot, int64_t P, int64_t T, int flags) {
     if (P < 0 || T < 0) return 0;
     switch (robot) {
-        case ROBOT_FETCH: return ws_bytes<Fetch>(P, T);
-        case ROBOT_FETCH_ARM: return ws_bytes<FetchArm>(P, T);
-        case ROBOT_PANDA: return ws_bytes<Panda>(P, T);
+        case ROBOT_FETCH: return ws_bytes<Fetch>(P, T, flags);
+        case ROBOT_FETCH_ARM: return ws_bytes<FetchArm>(P, T, flags);
+        case ROBOT_PANDA: return ws_bytes<Panda>(P, T, flags);
         default: return 0;
     }
 }
 
+extern "C" size_t cppflow_lm_full_workspace_bytes(int robot, int64_t P, int64_t T) {
+    return cppflow_lm_full_workspace_bytes_ex(robot, P, T, 0);
+}
+
 static int check_common(int robot, const cppflow_lm_params* params, int64_t P, int64_t T, const void* d_workspace,
-                        size_t workspace_bytes) {
+                        size_t workspace_bytes, int flags = 0) {
     CPPFLOW_CHECK_ARG(params != nullptr, "params");
     CPPFLOW_CHECK_ARG(P >= 0 && T >= 0, "P, T");
     CPPFLOW_CHECK_ARG(T <= 65535 && P <= (int64_t)1 << 30, "T must be <= 65535 (grid.y) and P <= 2^30");
@@ -1409,9 +1459,9 @@ static int check_common(int robot, const cppflow_lm_params* params, int64_t P, i
     CPPFLOW_CHECK_ARG(!params->use_virtual_configs || (params->n_virtual_configs > 0 && 2 * params->n_virtual_configs < T),
                       "2 * n_virtual_configs must be < T (optimization_utils.py:457-459)");
     CPPFLOW_CHECK_ARG(((uintptr_t)d_workspace & 15) == 0, "workspace must be 16-byte aligned");
-    if (workspace_bytes < cppflow_lm_full_workspace_bytes(robot, P, T))
+    if (workspace_bytes < cppflow_lm_full_workspace_bytes_ex(robot, P, T, flags))
         return fail(CPPFLOW_E_WORKSPACE, "lm_full: workspace too small (%zu < %zu)", workspace_bytes,
-                    cppflow_lm_full_workspace_bytes(robot, P, T));
+                    cppflow_lm_full_workspace_bytes_ex(robot, P, T, flags));
     return CPPFLOW_OK;
 }
 
@@ -1437,7 +1487,7 @@ extern "C" int cppflow_lm_full_solve(int robot, const cppflow_lm_params* params,
                                      int do_clamp, void* d_workspace, size_t workspace_bytes, float* d_x_out,
                                      void* stream) {
     if (P == 0 || T == 0) return CPPFLOW_OK;
-    if (int rc = check_common(robot, params, P, T, d_workspace, workspace_bytes)) return rc;
+    if (int rc = check_common(robot, params, P, T, d_workspace, workspace_bytes, do_clamp)) return rc;
     CPPFLOW_CHECK_ARG(d_q && d_x_out, "null pointer");
     int rc = CPPFLOW_OK;
     CPPFLOW_DISPATCH_ROBOT(robot, rc = launch_solve<M>(params, d_q, P, T, do_clamp, (float*)d_workspace, d_x_out,

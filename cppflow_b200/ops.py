@@ -33,6 +33,12 @@ ROBOT_IDS = {"fetch": 0, "fetch_arm": 1, "panda": 2}
 LM_CLAMP, LM_OVERLAP, LM_FUSED = 1, 2, 4  # CPPFLOW_LM_CLAMP / _OVERLAP / _FUSED (include/cppflow_b200.h)
 
 
+def lm_segments(n: int) -> int:
+    """CPPFLOW_LM_SEGMENTS(n): the flag bits that ask for the segmented solve with n time segments (0: twisted solve)."""
+    assert 0 <= n <= 255, "segments must be in [0, 255]"
+    return (n & 0xFF) << 8
+
+
 def _info(robot_id: int) -> _lib.RobotInfoC:
     info = _lib.RobotInfoC()
     check(_lib.load().cppflow_robot_info_get(robot_id, info))
@@ -235,9 +241,10 @@ def _workspace(device, nbytes: int, key: str) -> torch.Tensor:
 def lm_full_step(rid: int, ndof: int, params: LmParamsC, q: torch.Tensor, xv: Optional[torch.Tensor],
                  target: Optional[torch.Tensor], P: int, T: int, ob: Optional[Obstacles], clamp: bool,
                  out: Optional[torch.Tensor] = None, overlap: bool = False,
-                 workspace: Optional[torch.Tensor] = None, fused: bool = False) -> torch.Tensor:
+                 workspace: Optional[torch.Tensor] = None, fused: bool = False, segments: int = 0) -> torch.Tensor:
     """levenberg_marquardt_full (+ clamp) for P paths of T waypoints on the current stream.  `fused`: CPPFLOW_LM_FUSED
-    (elimination inside the assembly kernel, same bits).  `overlap`: launch the
+    (elimination inside the assembly kernel, same bits).  `segments`: CPPFLOW_LM_SEGMENTS (parallel-in-time solve for
+    few paths, csrc/lm_segsolve.cuh; rounding-level differences, larger workspace).  `overlap`: launch the
     solve with CPPFLOW_LM_OVERLAP (footprint that fits next to an assembly CTA, high launch priority) - for callers that run several chunks
     of paths on several streams (pipeline.ResidentPipeline), which must also pass one `workspace` per stream."""
     q = _check_q(q, ndof)
@@ -249,7 +256,8 @@ def lm_full_step(rid: int, ndof: int, params: LmParamsC, q: torch.Tensor, xv: Op
         target = require_cuda(target, "target_path")
         assert target.shape == (T, 7), f"target_path must be [{T}, 7], is {tuple(target.shape)}"
     lib = _lib.load()
-    nbytes = lib.cppflow_lm_full_workspace_bytes(rid, P, T)
+    flags = (LM_CLAMP if clamp else 0) | (LM_OVERLAP if overlap else 0) | (LM_FUSED if fused else 0) | lm_segments(segments)
+    nbytes = lib.cppflow_lm_full_workspace_bytes_ex(rid, P, T, flags)
     if workspace is None:
         ws = _workspace(q.device, nbytes, "lm_full")
     else:
@@ -257,7 +265,6 @@ def lm_full_step(rid: int, ndof: int, params: LmParamsC, q: torch.Tensor, xv: Op
         assert ws.is_cuda and ws.dtype == torch.uint8 and ws.numel() >= nbytes, "workspace too small"
     x_out = torch.empty_like(q) if out is None else out
     cu, tc, no = _obs(ob)
-    flags = (LM_CLAMP if clamp else 0) | (LM_OVERLAP if overlap else 0) | (LM_FUSED if fused else 0)
     check(lib.cppflow_lm_full_step(rid, params, ptr(q), ptr(xv), ptr(target), P, T, cu, tc, no, flags, ptr(ws),
                                    ws.numel(), ptr(x_out), stream_ptr(q.device)))
     return x_out

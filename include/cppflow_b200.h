@@ -83,7 +83,7 @@ const char* cppflow_last_error(void);
  * cppflow_robot_info, cppflow_constraints, cppflow_lm_loop_result, cppflow_lm_loop_job (as many as fit in n).
  * Returns the number of values the library knows (6).  A binding compares them with its own struct sizes after
  * dlopen and refuses a library built from another header. */
-#define CPPFLOW_ABI_VERSION 3
+#define CPPFLOW_ABI_VERSION 4
 int cppflow_abi_info(int64_t* out, int n);
 
 /* jrl.Robot properties (ndof, actuated_joints_limits, prismatic_joint_idxs, _collision_capsules_by_link). */
@@ -164,6 +164,17 @@ int cppflow_lm_full_solve(int robot, const cppflow_lm_params* params, const floa
  * runs from CTA to CTA through L2), so the (A, b) blocks never reach HBM; the solve then only back-substitutes.  Same
  * results bit for bit. */
 #define CPPFLOW_LM_FUSED 4
+/* cppflow_lm_full_step / cppflow_lm_full_solve: bits 8..15 of `do_clamp` ask for the SEGMENTED solve with that many
+ * time segments per path (csrc/lm_segsolve.cuh): the segments between S - 1 separator waypoints are eliminated in
+ * parallel, the separators' reduced block-tridiagonal system is solved, the segments are back-substituted in parallel.
+ * For few paths (<= ~2000) the twisted solve's dependent chain of T steps is the whole solve time; this one's chain is
+ * ~ T / S heavy + S + T / S light steps.  The result differs from the twisted solve's by rounding only and depends on
+ * S, not on P or the chunking.  S is reduced to T / 4 for short paths (fewer than 2 segments: the twisted solve).
+ * Needs the larger workspace of cppflow_lm_full_workspace_bytes_ex(robot, P, T, flags).  Ignored with
+ * CPPFLOW_LM_FUSED. */
+#define CPPFLOW_LM_SEGMENTS_SHIFT 8
+#define CPPFLOW_LM_SEGMENTS(n) (((n) & 0xff) << CPPFLOW_LM_SEGMENTS_SHIFT)
+size_t cppflow_lm_full_workspace_bytes_ex(int robot, int64_t P, int64_t T, int flags);
 
 /* run_lm_alternating_loss for ONE path (optimization.py:147-373; called by run_lm_optimization :376-426 with
  * ALT_LOSS_V2_1_DIFF / ALT_LOSS_V2_1_POSE): pose-only steps until the position and rotation errors are inside the

@@ -48,6 +48,12 @@ def test_error_codes_without_gpu():
     # (path blocks of 256) x 2 sides x 8 warps + 64 ints
     assert lib.cppflow_lm_full_workspace_bytes(0, 8192, 300) == 8192 * 300 * 44 * 4 + (32 * 2 * 8 + 64) * 4
     assert lib.cppflow_lm_full_workspace_bytes(2, 10, 20) == 16 * 20 * 36 * 4 + (1 * 2 * 8 + 64) * 4
+    # segmented solve (16 segments): + factor area (= blocks) + corners (2 sides x 27 float4 per segment) + 15 separators
+    base = 16 * 300 * 44 * 4 + (1 * 2 * 8 + 64) * 4
+    assert lib.cppflow_lm_full_workspace_bytes_ex(0, 16, 300, 16 << 8) == (
+        (base + 255) // 256 * 256 + 16 * 300 * 44 * 4 + 16 * 2 * 27 * 16 * 16 + 15 * 2 * 16 * 16)
+    assert lib.cppflow_lm_full_workspace_bytes_ex(0, 16, 300, 0) == base
+    assert lib.cppflow_lm_full_workspace_bytes_ex(0, 16, 6, 16 << 8) == lib.cppflow_lm_full_workspace_bytes(0, 16, 6)
     assert lib.cppflow_dp_search_workspace_bytes(175, 295) >= 4 * (295 * 175 + 294 * 175 * 175)
     with pytest.raises(_lib.CppflowError):
         _lib.check(-1)

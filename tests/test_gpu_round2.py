@@ -544,3 +544,95 @@ def test_fused_elimination_equals_two_kernel_step(robots, r):
             got2 = ops.lm_full_step(rob.robot_id, rob.ndof, prm, x, xv, tg, P, T, ob, False, fused=True, overlap=True)
             ref2 = ops.lm_full_step(rob.robot_id, rob.ndof, prm, x, xv, tg, P, T, ob, False)
             assert torch.equal(got2, ref2), (r, P, T, name, "no clamp / overlap variant")
+
+
+def _dense_step_fp64(lib, rob, prm, pm, x, tg, ob_args, P, T, paths):
+    """fp64 solution of the normal equations the assembly kernel wrote, for a few paths: reads the packed (A_tt, b_t) blocks
+    ([16-path group][t][float4 k][path in group]) back and solves the block-tridiagonal system densely."""
+    from cppflow_b200 import _lib
+
+    D = rob.ndof
+    NT = D * (D + 1) // 2
+    NW = (NT + D + 3) // 4 * 4
+    ws = torch.zeros((lib.cppflow_lm_full_workspace_bytes(rob.robot_id, P, T),), device=DEV, dtype=torch.uint8)
+    cu, tc, no = ob_args
+    _lib.check(lib.cppflow_lm_full_assemble(rob.robot_id, prm, _lib.ptr(x), None, _lib.ptr(tg), P, T, cu, tc, no,
+                                            _lib.ptr(ws), ws.numel(), _lib.stream_ptr(DEV)))
+    torch.cuda.synchronize()
+    groups = (P + 15) // 16
+    blocks = ws.view(torch.float32)[: groups * T * NW * 16].cpu().numpy().reshape(groups, T, NW // 4, 16, 4)
+    beta = np.array([(pm.alpha_differencing * (pm.alpha_differencing_prismatic_scaling if d in rob.prismatic_joint_idxs else 1.0)) ** 2
+                     for d in range(D)]) * (1.0 if pm.use_differencing else 0.0)
+    out = {}
+    for p in paths:
+        blk = blocks[p // 16, :, :, p % 16, :].reshape(T, NW).astype(np.float64)
+        Mx = np.zeros((T * D, T * D))
+        for i in range(D):
+            for j in range(i + 1):
+                for t in range(T):
+                    Mx[t * D + i, t * D + j] = Mx[t * D + j, t * D + i] = blk[t, i * (i + 1) // 2 + j]
+        for t in range(T - 1):
+            for d in range(D):
+                Mx[t * D + d, (t + 1) * D + d] = Mx[(t + 1) * D + d, t * D + d] = -beta[d]
+        rhs = blk[:, NT:NT + D].reshape(-1)
+        out[p] = (Mx, rhs, np.linalg.solve(Mx, rhs))
+    return out
+
+
+@pytest.mark.parametrize("r", ROBOTS)
+def test_segmented_solve_equals_twisted_solve_up_to_rounding(robots, r):
+    """CPPFLOW_LM_SEGMENTS (csrc/lm_segsolve.cuh): segments between separator waypoints eliminated in parallel, the
+    separators' reduced system, parallel back-substitution.  Another elimination order of the same linear system.  With
+    every term on the system is ill-conditioned (lambda = 1e-6: condition number ~ 3e7), so BOTH float32 solves sit
+    ~1e-2 rad from the fp64 solution of the same blocks in the null-space directions; the yardsticks are therefore the
+    residual of the normal equations and the distance from the fp64 solution, each against the twisted solve's own.
+    For a given segment count the result of a path does NOT depend on how many paths are solved with it (bit-exact),
+    and short paths fall back to the twisted solve."""
+    from cppflow_b200 import ops, _lib
+    from cppflow_b200.lm_hyper_parameters import all_terms_parameters, ALT_LOSS_V2_1_DIFF
+
+    rob = robots[r]
+    cuboids, Tcuboids = cuboid_tensors(OBSTACLES[r])
+    ob = ops.Obstacles(cuboids, Tcuboids)
+    lib = _lib.load()
+    worst = {"residual": 0.0, "energy": 0.0, "distance_all": 0.0, "distance_diff": 0.0}
+    for P, T in ((1, 300), (20, 301), (48, 37), (5, 9), (33, 8), (3, 7), (1100, 64)):
+        m, target, x0 = synthetic_problem(r, P, T, seed=P + T)
+        x, tg = x0.to(DEV), target.to(DEV)
+        for name, pm in (("all", all_terms_parameters()), ("diff", ALT_LOSS_V2_1_DIFF)):
+            if pm.use_virtual_configs and 2 * pm.n_virtual_configs >= T:
+                continue
+            prm = ops.make_params(pm)
+            ref = ops.lm_full_step(rob.robot_id, rob.ndof, prm, x, None, tg, P, T, ob, False)
+            paths = sorted({0, P // 2, P - 1})
+            dense = _dense_step_fp64(lib, rob, prm, pm, x, tg, ops._obs(ob), P, T, paths)
+
+            def quality(res, p):
+                Mx, rhs, sol = dense[p]
+                dx = (res[p * T:(p + 1) * T] - x[p * T:(p + 1) * T]).double().cpu().numpy().reshape(-1)
+                e = dx - sol
+                return np.linalg.norm(Mx @ dx - rhs) / np.linalg.norm(rhs), np.abs(e).max(), float(e @ Mx @ e) / float(sol @ Mx @ sol)
+
+            for S in (2, 3, 5, 16, 200):
+                got = ops.lm_full_step(rob.robot_id, rob.ndof, prm, x, None, tg, P, T, ob, False, segments=S)
+                if T // 4 < 2:
+                    assert torch.equal(got, ref), (r, P, T, name, S, "short path: twisted solve")
+                    continue
+                for p in paths:
+                    (res_t, err_t, en_t), (res_s, err_s, en_s) = quality(ref, p), quality(got, p)
+                    worst["residual"] = max(worst["residual"], res_s / (res_t + 1e-7))
+                    worst["energy"] = max(worst["energy"], en_s / (en_t + 1e-13))
+                    worst["distance_" + name] = max(worst["distance_" + name], err_s / (err_t + 2e-5))
+                    assert res_s <= 3.0 * res_t + 1e-6, (r, P, T, name, S, p, "residual", res_s, res_t)
+                    # error in the energy norm of the normal equations (what the LM step minimises), relative to the step
+                    assert en_s <= 10.0 * en_t + 1e-12, (r, P, T, name, S, p, "energy-norm error", en_s, en_t)
+                    if name == "diff":  # well-conditioned: also element-wise
+                        assert err_s <= 3.0 * err_t + 2e-5, (r, P, T, name, S, p, "distance from fp64", err_s, err_t)
+                # one path alone = the same path among the others
+                one = ops.lm_full_step(rob.robot_id, rob.ndof, prm, x[-T:].contiguous(), None, tg, 1, T, ob, False, segments=S)
+                assert torch.equal(one, got[-T:]), (r, P, T, name, S, "path count changes the result")
+            clamped = ops.lm_full_step(rob.robot_id, rob.ndof, prm, x, None, tg, P, T, ob, True, segments=5)
+            unclamped = ops.lm_full_step(rob.robot_id, rob.ndof, prm, x, None, tg, P, T, ob, False, segments=5)
+            lim = torch.tensor(rob.actuated_joints_limits, device=DEV, dtype=torch.float32)
+            assert torch.equal(clamped, torch.minimum(torch.maximum(unclamped, lim[:, 0]), lim[:, 1]))
+    print("segmented / twisted, worst ratios:", r, {k: round(v, 2) for k, v in worst.items()})
