@@ -428,24 +428,37 @@ def main():
     # ---- strong scaling: the SAME P paths split over the ranks (P / N per GPU), K steps, no tail
     strong = None
     sizes = sorted({max(16, P // n) for n in (2, 4, 8)} | ({max(16, P // world)} if world > 1 else set()), reverse=True)
-    per_size = {}
+    per_size, per_size_twisted, seg_of = {}, {}, {}
     for n_paths in sizes:
         s0, _ = shard_range(P, rank % max(1, P // n_paths), max(1, P // n_paths))
         xs = x0[s0 * T:(s0 + n_paths) * T]
-        pipe_s = ResidentPipeline(problem, n_paths, all_terms_parameters())
-        time_pipeline(pipe_s, xs, x_out[: n_paths * T], warmup, barrier)
-        per_size[n_paths] = max_over_ranks(time_pipeline(pipe_s, xs, x_out[: n_paths * T], steps, barrier)[0]) / steps
+        # few paths per GPU: the solve's chain of T dependent steps is most of the iteration -> the segmented
+        # (parallel-in-time) solve, chosen by path count (pipeline.ResidentPipeline segments="auto"); the twisted solve's
+        # time at the same size is reported beside it
+        for seg, dst in (("auto", per_size), (0, per_size_twisted)):
+            if seg == 0 and seg_of.get(n_paths) == 0:
+                dst[n_paths] = per_size[n_paths]  # "auto" already was the twisted solve
+                continue
+            pipe_s = ResidentPipeline(problem, n_paths, all_terms_parameters(), segments=seg)
+            seg_of.setdefault(n_paths, pipe_s.segments)
+            time_pipeline(pipe_s, xs, x_out[: n_paths * T], warmup, barrier)
+            dst[n_paths] = max_over_ranks(time_pipeline(pipe_s, xs, x_out[: n_paths * T], steps, barrier)[0]) / steps
     if world > 1:
         ms_strong = per_size[max(16, P // world)]
         strong = {"paths_total": P, "paths_per_gpu": max(16, P // world), "ms_per_step": ms_strong,
                   "evals_per_s": evals_per_step / (ms_strong * 1e-3),
                   "efficiency": ms_steps_only / (world * ms_strong),
+                  "solve_segments": seg_of[max(16, P // world)],
+                  "ms_per_step_twisted_solve": per_size_twisted[max(16, P // world)],
+                  "efficiency_twisted_solve": ms_steps_only / (world * per_size_twisted[max(16, P // world)]),
                   "what": "same 8192 x 300 workload split P/N per GPU, K pipelined steps, max over ranks; efficiency = "
                           "t(P paths on one GPU, measured in this run) / (N * t(P/N paths per GPU))"}
     strong_preview = {
         "what": "per-GPU step time with P/n paths resident (paths are independent and no data-path collective exists, so "
                 "this is the n-GPU strong-scaling step time); efficiency = t(P) / (n * t(P/n))",
         "ms_per_step": {str(n): per_size[n] for n in sizes},
+        "solve_segments": {str(n): seg_of[n] for n in sizes},
+        "ms_per_step_twisted_solve": {str(n): per_size_twisted[n] for n in sizes},
         "efficiency": {f"1/{P // n}": ms_steps_only / ((P // n) * per_size[n]) for n in sizes},
     }
 

@@ -22,6 +22,17 @@ namespace {
 
 inline size_t align256(size_t n) { return (n + 255) / 256 * 256; }
 
+// The differencing step of ONE path is the block solve's dependent chain and nothing else: it takes the segmented
+// solve (csrc/lm_segsolve.cuh; 0.098 -> 0.046 ms for T = 300).  CPPFLOW_LOOP_SEGMENTS = 0 restores the twisted solve.
+inline int loop_step_flags() {
+    static const int segments = [] {
+        const char* e = std::getenv("CPPFLOW_LOOP_SEGMENTS");
+        const int n = e ? std::atoi(e) : 16;
+        return n < 0 ? 0 : n > 255 ? 255 : n;
+    }();
+    return CPPFLOW_LM_CLAMP | CPPFLOW_LM_SEGMENTS(segments);
+}
+
 struct LoopLayout {
     size_t x_bytes, off_xa, off_xb, off_valid, off_metrics, off_lm, total;
     LoopLayout(int robot, int ndof, int64_t T) {
@@ -32,7 +43,7 @@ struct LoopLayout {
         off_valid = off_xb + x_bytes;
         off_metrics = off_valid + x_bytes;
         off_lm = off_metrics + 256;
-        total = off_lm + align256(cppflow_lm_full_workspace_bytes(robot, 1, T));
+        total = off_lm + align256(cppflow_lm_full_workspace_bytes_ex(robot, 1, T, loop_step_flags()));
     }
 };
 
@@ -118,7 +129,7 @@ struct LoopState {
         if (pose_pos_valid && pose_rot_valid) {
             // virtual configs = the current iterate (:253): their residual is identically zero -> d_xv = NULL
             if (int rc = cppflow_lm_full_step(j->robot, j->params_diff, x_cur, nullptr, j->d_target, 1, j->T, j->h_cuboids,
-                                              j->h_Tcuboids, j->n_obstacles, CPPFLOW_LM_CLAMP, lm_ws, lm_ws_bytes, x_new, j->stream))
+                                              j->h_Tcuboids, j->n_obstacles, loop_step_flags(), lm_ws, lm_ws_bytes, x_new, j->stream))
                 return rc;
             was_differencing = true;
         } else if (fuse_pose && j->T <= 1024) {

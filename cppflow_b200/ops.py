@@ -33,6 +33,16 @@ ROBOT_IDS = {"fetch": 0, "fetch_arm": 1, "panda": 2}
 LM_CLAMP, LM_OVERLAP, LM_FUSED = 1, 2, 4  # CPPFLOW_LM_CLAMP / _OVERLAP / _FUSED (include/cppflow_b200.h)
 
 
+def loop_segments() -> int:
+    """Segments of the single-path full step (the differencing step of run_lm_alternating_loss): the native loop
+    (csrc/lm_loop.cu: loop_step_flags) and the Python loop must take the same solve to return the same bits.
+    CPPFLOW_LOOP_SEGMENTS = 0 restores the twisted solve in both."""
+    import os
+
+    n = int(os.environ.get("CPPFLOW_LOOP_SEGMENTS", "16"))
+    return min(max(n, 0), 255)
+
+
 def lm_segments(n: int) -> int:
     """CPPFLOW_LM_SEGMENTS(n): the flag bits that ask for the segmented solve with n time segments (0: twisted solve)."""
     assert 0 <= n <= 255, "segments must be in [0, 255]"

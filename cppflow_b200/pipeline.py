@@ -235,8 +235,13 @@ class ResidentPipeline:
     Chunks are multiples of 256 paths (the assembly CTA) where P allows."""
 
     def __init__(self, problem: Problem, n_paths: int, params: Optional[OptimizationParameters] = None,
-                 n_chunks: Optional[int] = None, device=None, overlap: bool = True, solve_sms: Optional[int] = None):
-        """`solve_sms`: instead of sharing SMs, give the block solves `solve_sms` SMs of their own (a green-context
+                 n_chunks: Optional[int] = None, device=None, overlap: bool = True, solve_sms: Optional[int] = None,
+                 segments=0):
+        """`segments`: time segments of the segmented solve (CPPFLOW_LM_SEGMENTS, csrc/lm_segsolve.cuh; 0 = the twisted
+        solve).  For <= ~2000 paths per GPU the twisted solve's chain of T dependent steps is most of the iteration; the
+        segmented solve's result differs by rounding and depends on `segments` only, not on the chunking.  "auto": 16
+        segments up to 2048 paths (where it is faster), the twisted solve above.
+        `solve_sms`: instead of sharing SMs, give the block solves `solve_sms` SMs of their own (a green-context
         partition) and the assembly the rest: the solves then run at their stand-alone speed and displace nothing."""
         self.problem = problem
         self.robot = problem.robot
@@ -245,6 +250,13 @@ class ResidentPipeline:
         self.device = problem.target_path.device if device is None else torch.device(device)
         self.prm = ops.make_params(params if params is not None else all_terms_parameters())
         self.overlap = overlap
+        if segments == "auto":
+            # tools/probe_segpipe.py, ms per iteration at T = 300, twisted (default chunking) against 16 segments:
+            #   256 paths 0.163 / 0.077   512: 0.171 / 0.093   1024: 0.197 / 0.139   2048: 0.280 / 0.227   4096: 0.372 / 0.42
+            segments = 16 if n_paths <= 2048 else 0
+        self.segments = segments
+        if n_chunks is None and segments:
+            n_chunks = 1 if n_paths <= 256 else 2  # 512: 0.098 / 0.093 (1 / 2 chunks), 1024: 0.151 / 0.139, 2048: 0.262 / 0.229
         if n_chunks is None:
             # measured at T = 300, K = 20 (tools/probe_timeline.py, ms per iteration by chunk count 1 / 2 / 3 / 4 / 6):
             #   8192 paths: - / - / - / 0.518 / 0.509      4096: 0.387 / 0.407 / 0.416 / 0.422 / 0.415
@@ -265,8 +277,8 @@ class ResidentPipeline:
         else:
             self.streams = [torch.cuda.Stream(self.device) for _ in self.chunks]
         lib = ops._lib.load()
-        self.ws = [torch.empty((lib.cppflow_lm_full_workspace_bytes(self.robot.robot_id, n, self.T),), device=self.device,
-                               dtype=torch.uint8) for _, n in self.chunks]
+        self.ws = [torch.empty((lib.cppflow_lm_full_workspace_bytes_ex(self.robot.robot_id, n, self.T, ops.lm_segments(segments)),),
+                               device=self.device, dtype=torch.uint8) for _, n in self.chunks]
 
     def _all_streams(self):
         return self.streams + (self.solve_streams if self.partition is not None else [])
@@ -291,7 +303,7 @@ class ResidentPipeline:
         if self.partition is not None:
             lib = ops._lib.load()
             cu, tc, no = ops._obs(self.problem.obstacle_tables)
-            flags = (ops.LM_CLAMP if clamp else 0) | (ops.LM_OVERLAP if self.overlap else 0)  # overlap: the 4-slot ring
+            flags = (ops.LM_CLAMP if clamp else 0) | (ops.LM_OVERLAP if self.overlap else 0) | ops.lm_segments(self.segments)  # overlap: the 4-slot ring
             for c, ((p0, n), ws) in enumerate(zip(self.chunks, self.ws)):
                 sl = slice(p0 * T, (p0 + n) * T)
                 sa, ss = self.streams[c], self.solve_streams[c]
@@ -308,7 +320,7 @@ class ResidentPipeline:
         # chunks that is a quarter of the step)
         lib = ops._lib.load()
         cu, tc, no = ops._obs(self.problem.obstacle_tables)
-        flags = (ops.LM_CLAMP if clamp else 0) | (ops.LM_OVERLAP if self.overlap else 0)
+        flags = (ops.LM_CLAMP if clamp else 0) | (ops.LM_OVERLAP if self.overlap else 0) | ops.lm_segments(self.segments)
         assert x.is_cuda and out.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
         tgt = ops.ptr(self.problem.target_path)
         with torch.cuda.device(self.device):
