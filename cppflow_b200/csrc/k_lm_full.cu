@@ -1368,11 +1368,17 @@ static int launch_solve_segmented(const SolveParams& sp, const float* q, int64_t
     const SegGeom geo{(int)T, S};
     const int64_t warps = (P + 15) / 16 * S;
     constexpr int W = 1;  // single-warp CTAs spread the chains over the SMs' schedulers (as the register-resident solve)
+    static const int passes = [] {  // debug (tools/probe_segsolve.py): stop after pass 1 / 2 to time the passes live
+        const char* e = std::getenv("CPPFLOW_SEG_PASSES");
+        return e ? std::atoi(e) : 3;
+    }();
     lm_seg_eliminate_kernel<M, W><<<grid_for(warps, W), 32 * W, 0, st>>>(P, geo, sp, ws, fac, corners);
-    const size_t sh = (size_t)(S - 1) * seg_node_floats<M::NDOF>() * sizeof(float);
+    if (passes < 2) return CPPFLOW_OK;
+    const size_t sh = seg_reduced_smem<M::NDOF>(S);
     static SmemGrant granted;  // per template instantiation and device
-    if (int rc = ensure_dynamic_smem(lm_seg_reduced_kernel<M>, (size_t)(SEG_MAX_SEGMENTS - 1) * seg_node_floats<M::NDOF>() * sizeof(float), granted)) return rc;
-    lm_seg_reduced_kernel<M><<<grid_for(P, 16), 32 * SEG_REDUCED_WARPS, sh, st>>>(q, P, geo, sp, ws, corners, sepx, x_out);
+    if (int rc = ensure_dynamic_smem(lm_seg_reduced_kernel<M>, seg_reduced_smem<M::NDOF>(SEG_MAX_SEGMENTS), granted)) return rc;
+    lm_seg_reduced_kernel<M><<<grid_for(P, 16), 32 * SEG_REDUCED_WARPS, sh, st>>>(P, geo, sp, ws, corners, sepx);
+    if (passes < 3) return CPPFLOW_OK;
     lm_seg_substitute_kernel<M, W><<<grid_for(warps, W), 32 * W, 0, st>>>(q, P, geo, sp, ws, fac, sepx, x_out);
     return CPPFLOW_OK;
 }

@@ -25,6 +25,7 @@
 //
 // Included by k_lm_full.cu after BlockLayout / SolveParams / BetaSel.
 #pragma once
+#include <type_traits>
 
 namespace cppflow {
 
@@ -149,15 +150,44 @@ lm_seg_eliminate_kernel(int64_t P, SegGeom geo, const SolveParams prm, const flo
 #pragma unroll
     for (int i = 0; i < R0 * D; ++i) Q[i] = (side * R0 + i / D == i % D) ? 1.f : 0.f;
 
+    // Q <- Q (S^-1 beta): row i of Q times the symmetric G = -nS of the up lane, column j scaled by beta_j
+    float G[NT];
+    auto q_update = [&]() {
+#pragma unroll
+        for (int i = 0; i < R0; ++i) {
+            float r[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int c = 0; c < D; c += 2) {
+                    a0 = fmaf(Q[i * D + c], (c <= j ? G[tri(j, c)] : G[tri(c, j)]), a0);
+                    if (c + 1 < D) a1 = fmaf(Q[i * D + c + 1], (c + 1 <= j ? G[tri(j, c + 1)] : G[tri(c + 1, j)]), a1);
+                }
+                r[j] = a0 + a1;
+            }
+            static_for<D>([&](auto Jj) {
+                constexpr int j = decltype(Jj)::value;
+                Q[i * D + j] = -bs.template b<j>() * r[j];
+            });
+        }
+    };
     float nxt[NW];
     ld_lane<NV>(wsg + t_of(0) * LY::blk_f4(), nxt);
-    for (int k = 0; k < L; ++k) {
+    // one elimination step; WITH_Q: the Q update of the PREVIOUS step sits in the same basic block as this step's sweep
+    // (it does not depend on it), so its 256 FMAs fill the issue slots the sweep's reciprocal chain leaves empty
+    auto step = [&](int k, auto with_q, auto keep_g) {
         const int t = t_of(k);
         float blk[NW];
 #pragma unroll
         for (int i = 0; i < NW; ++i) blk[i] = nxt[i];
         if (k + 1 < L) ld_lane<NV>(wsg + t_of(k + 1) * LY::blk_f4(), nxt);
+        if constexpr (decltype(with_q)::value) q_update();
         seg_eliminate<M>(bs, blk, nS, u, prm.pivot_floor);
+        if constexpr (decltype(keep_g)::value) {
+#pragma unroll
+            for (int i = 0; i < NT; ++i) G[i] = __shfl_sync(0xffffffffu, nS[i], lane & ~1);
+        }
         if (side == 0 ? t < mid : t > mid) {
             float v[NW];
 #pragma unroll
@@ -168,30 +198,13 @@ lm_seg_eliminate_kernel(int64_t P, SegGeom geo, const SolveParams prm, const flo
             for (int i = NT + D; i < NW; ++i) v[i] = 0.f;
             st_lane<NV>(facg + t * LY::blk_f4(), v);
         }
-        if (interior) {
-            // Q <- Q (S^-1 beta): row i of Q times the symmetric -nS of the up lane, column j scaled by beta_j
-            float G[NT];
-#pragma unroll
-            for (int i = 0; i < NT; ++i) G[i] = __shfl_sync(0xffffffffu, nS[i], lane & ~1);
-#pragma unroll
-            for (int i = 0; i < R0; ++i) {
-                float r[D];
-#pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-                    for (int c = 0; c < D; c += 2) {
-                        a0 = fmaf(Q[i * D + c], (c <= j ? G[tri(j, c)] : G[tri(c, j)]), a0);
-                        if (c + 1 < D) a1 = fmaf(Q[i * D + c + 1], (c + 1 <= j ? G[tri(j, c + 1)] : G[tri(c + 1, j)]), a1);
-                    }
-                    r[j] = a0 + a1;
-                }
-                static_for<D>([&](auto Jj) {
-                    constexpr int j = decltype(Jj)::value;
-                    Q[i * D + j] = -bs.template b<j>() * r[j];
-                });
-            }
-        }
+    };
+    if (interior) {
+        step(0, std::false_type{}, std::true_type{});
+        for (int k = 1; k < L; ++k) step(k, std::true_type{}, std::true_type{});
+        q_update();
+    } else {
+        for (int k = 0; k < L; ++k) step(k, std::false_type{}, std::false_type{});
     }
     // corner record of this (segment, side): (nS, u) of the last block eliminated, then Q
     float4* cg = reinterpret_cast<float4*>(corners) + ((g * geo.S + seg) * 2 + side) * LY::corner_f4() + l;
@@ -233,12 +246,15 @@ constexpr int SEG_REDUCED_WARPS = 8;
 
 template <int D>
 constexpr int seg_node_floats() { return (BlockLayout<D>::NW + D * D) * 16; }  // [NW + D*D][16 paths]
+template <int D>
+constexpr size_t seg_reduced_smem(int S) {  // the separators' nodes + one coupling term [NT + D][32 lanes]
+    return ((size_t)(S - 1) * seg_node_floats<D>() + (size_t)(BlockLayout<D>::NT + D) * 32) * sizeof(float);
+}
 
 template <class M>
 __global__ void __launch_bounds__(32 * SEG_REDUCED_WARPS, 1)
-lm_seg_reduced_kernel(const float* __restrict__ q, int64_t P, SegGeom geo, const SolveParams prm,
-                      const float* __restrict__ ws, const float* __restrict__ corners, float* __restrict__ sepx,
-                      float* __restrict__ x_out) {
+lm_seg_reduced_kernel(int64_t P, SegGeom geo, const SolveParams prm, const float* __restrict__ ws,
+                      const float* __restrict__ corners, float* __restrict__ sepx) {
     constexpr int D = M::NDOF;
     using LY = SegLayout<D>;
     constexpr int NT = LY::NT, NW = LY::NW, NV = LY::NV;
@@ -280,16 +296,52 @@ lm_seg_reduced_kernel(const float* __restrict__ q, int64_t P, SegGeom geo, const
         }
     }
     __syncthreads();
-    if (warp != 0) return;
 
     const int side = lane & 1, l = lane >> 1;
-    const int64_t p_raw = g * 16 + l;
-    const bool active = p_raw < P;
-    const int64_t p = active ? p_raw : P - 1;
     const int m = n / 2;
     const int n_side = side == 0 ? m : n - 1 - m;
+    const int n_steps = m > n - 1 - m ? m : n - 1 - m;  // uniform: every warp meets every barrier
     auto node_of = [&](int k) { return side == 0 ? k : n - 1 - k; };
-    // C of the step from node `from` into its inner neighbour: up lane K_from, down lane K_{from-1}^T
+    float* contrib = seg_sm + n * NODE;  // [NT + D][32 lanes]: the coupling term of the step being taken
+    // The step into a node costs C^T (nS C) (two D x D x D products) before its sweep can start: the eight warps take one
+    // COLUMN c of it each (same lane <-> (path, side) mapping in every warp), warp 0 adds the columns to the node's block
+    // and sweeps.  Term of the eliminated node `from` for its inner neighbour, C = the block (from, inner):
+    //     contrib[tri(i, c)] = (C^T (nS C))_ic  (i >= c),   contrib[NT + c] = -(C^T u)_c,   nS = -S_from^-1
+    auto contribute = [&](int from, int c) {
+        const float* nd = seg_sm + from * NODE + l;
+        const float* K = seg_sm + (side == 0 ? from : from - 1) * NODE + NW * 16 + l;  // up lane K_from, down lane K_{from-1}^T
+        auto Cel = [&](int i, int cc) { return K[(side == 0 ? i * D + cc : cc * D + i) * 16]; };
+        float nSin[NT], Cc[D], Pc[D];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) nSin[i] = nd[i * 16];
+#pragma unroll
+        for (int k = 0; k < D; ++k) Cc[k] = Cel(k, c);
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; k += 2) {
+                a0 = fmaf((k <= i ? nSin[tri(i, k)] : nSin[tri(k, i)]), Cc[k], a0);
+                if (k + 1 < D) a1 = fmaf((k + 1 <= i ? nSin[tri(i, k + 1)] : nSin[tri(k + 1, i)]), Cc[k + 1], a1);
+            }
+            Pc[i] = a0 + a1;
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; k += 2) {
+                a0 = fmaf(Cel(k, i), Pc[k], a0);
+                if (k + 1 < D) a1 = fmaf(Cel(k + 1, i), Pc[k + 1], a1);
+            }
+            if (i >= c) contrib[(i * (i + 1) / 2 + c) * 32 + lane] = a0 + a1;
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) acc = fmaf(-Cc[k], nd[(NT + k) * 16], acc);
+        contrib[(NT + c) * 32 + lane] = acc;
+    };
+    // C of the step from node `from` into its inner neighbour, whole (back-substitution)
     auto load_C = [&](int from, float (&C)[D * D]) {
         const float* K = seg_sm + (side == 0 ? from : from - 1) * NODE + NW * 16 + l;
 #pragma unroll
@@ -297,86 +349,51 @@ lm_seg_reduced_kernel(const float* __restrict__ q, int64_t P, SegGeom geo, const
 #pragma unroll
             for (int c = 0; c < D; ++c) C[i * D + c] = K[(side == 0 ? i * D + c : c * D + i) * 16];
     };
-    // (Sm, y) += (C^T (nS C), -C^T u): the Schur-complement term of an eliminated neighbour (nS = -S_in^-1)
-    auto couple = [&](const float (&nS)[NT], const float (&u)[D], const float (&C)[D * D], float (&Sm)[NT], float (&y)[D]) {
-#pragma unroll
-        for (int c = 0; c < D; ++c) {
-            float Pc[D];  // column c of nS C
-#pragma unroll
-            for (int i = 0; i < D; ++i) {
-                float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-                for (int k = 0; k < D; k += 2) {
-                    a0 = fmaf((k <= i ? nS[tri(i, k)] : nS[tri(k, i)]), C[k * D + c], a0);
-                    if (k + 1 < D) a1 = fmaf((k + 1 <= i ? nS[tri(i, k + 1)] : nS[tri(k + 1, i)]), C[(k + 1) * D + c], a1);
-                }
-                Pc[i] = a0 + a1;
-            }
-#pragma unroll
-            for (int i = c; i < D; ++i) {
-                float acc = Sm[tri(i, c)];
-#pragma unroll
-                for (int k = 0; k < D; ++k) acc = fmaf(C[k * D + i], Pc[k], acc);
-                Sm[tri(i, c)] = acc;
-            }
-            float acc = y[c];
-#pragma unroll
-            for (int k = 0; k < D; ++k) acc = fmaf(-C[k * D + c], u[k], acc);
-            y[c] = acc;
-        }
-    };
 
-    float nS[NT], u[D], C[D * D];
-    for (int k = 0; k < n_side; ++k) {
-        const int j = node_of(k);
-        float* node = seg_sm + j * NODE + l;
-        float Sm[NT], y[D];
+    for (int k = 0; k < n_steps; ++k) {
+        const bool valid = k < n_side;
+        if (k > 0 && valid && warp < D) contribute(node_of(k - 1), warp);
+        __syncthreads();
+        if (warp == 0 && valid) {
+            float* node = seg_sm + node_of(k) * NODE + l;
+            float nS[NT], u[D];
 #pragma unroll
-        for (int i = 0; i < NT; ++i) Sm[i] = node[i * 16];
+            for (int i = 0; i < NT; ++i) nS[i] = node[i * 16] + (k > 0 ? contrib[i * 32 + lane] : 0.f);
 #pragma unroll
-        for (int d = 0; d < D; ++d) y[d] = node[(NT + d) * 16];
-        if (k > 0) couple(nS, u, C, Sm, y);
+            for (int d = 0; d < D; ++d) u[d] = node[(NT + d) * 16] + (k > 0 ? contrib[(NT + d) * 32 + lane] : 0.f);
+            sweep_neg_inverse<D>(nS, u, prm.pivot_floor);
 #pragma unroll
-        for (int i = 0; i < NT; ++i) nS[i] = Sm[i];
+            for (int i = 0; i < NT; ++i) node[i * 16] = nS[i];
 #pragma unroll
-        for (int d = 0; d < D; ++d) u[d] = y[d];
-        sweep_neg_inverse<D>(nS, u, prm.pivot_floor);
-#pragma unroll
-        for (int i = 0; i < NT; ++i) node[i * 16] = nS[i];
-#pragma unroll
-        for (int d = 0; d < D; ++d) node[(NT + d) * 16] = u[d];
-        load_C(j, C);  // for the step into the next node (or the middle)
+            for (int d = 0; d < D; ++d) node[(NT + d) * 16] = u[d];
+        }
+        __syncthreads();
     }
-    __syncwarp();
-    // middle node: both sides' terms
-    float x[D];
+    if (n_side > 0 && warp < D) contribute(node_of(n_side - 1), warp);  // both sides' terms of the middle node
+    __syncthreads();
+    if (warp != 0) return;
+    float x[D], C[D * D];
     {
-        float W[NT], wy[D];
-#pragma unroll
-        for (int i = 0; i < NT; ++i) W[i] = 0.f;
-#pragma unroll
-        for (int d = 0; d < D; ++d) wy[d] = 0.f;
-        if (n_side > 0) couple(nS, u, C, W, wy);
         const float* node = seg_sm + m * NODE + l;
         float Sm[NT];
 #pragma unroll
-        for (int i = 0; i < NT; ++i) Sm[i] = node[i * 16] + (W[i] + __shfl_xor_sync(0xffffffffu, W[i], 1));
+        for (int i = 0; i < NT; ++i) {
+            const float w = n_side > 0 ? contrib[i * 32 + lane] : 0.f;
+            Sm[i] = node[i * 16] + (w + __shfl_xor_sync(0xffffffffu, w, 1));
+        }
 #pragma unroll
-        for (int d = 0; d < D; ++d) x[d] = node[(NT + d) * 16] + (wy[d] + __shfl_xor_sync(0xffffffffu, wy[d], 1));
+        for (int d = 0; d < D; ++d) {
+            const float w = n_side > 0 ? contrib[(NT + d) * 32 + lane] : 0.f;
+            x[d] = node[(NT + d) * 16] + (w + __shfl_xor_sync(0xffffffffu, w, 1));
+        }
         sweep_neg_inverse<D>(Sm, x, prm.pivot_floor);
     }
+    // the separators' dx go to `sepx`; pass 3 adds them to q (a global load here would stall the chain at every node)
     auto emit = [&](int j, const float (&xj)[D]) {
         float xs[LY::DQ];
 #pragma unroll
         for (int d = 0; d < LY::DQ; ++d) xs[d] = d < D ? xj[d] : 0.f;
         st_lane<LY::XV>(reinterpret_cast<float4*>(sepx) + (g * n + j) * LY::x_f4() + l, xs);
-        if (active) {
-            const int64_t t = geo.sep(j + 1);
-            float xn[D];
-#pragma unroll
-            for (int d = 0; d < D; ++d) xn[d] = __ldg(q + (p * geo.T + t) * D + d) + xj[d];
-            seg_store_x<M>(x_out + (p * geo.T + t) * D, xn, prm.do_clamp);
-        }
     };
     if (side == 0) emit(m, x);
     // back-substitution outwards: x_j = u_j + nS_j (C x_inner)
@@ -432,16 +449,23 @@ lm_seg_substitute_kernel(const float* __restrict__ q, int64_t P, SegGeom geo, co
     const BetaSel<M> bs(prm.b_rev, prm.b_pri);
     auto t_of = [&](int k) { return side == 0 ? a + k : e - k; };
 
-    // the separator this side faces (none at the ends of the path: coupling 0)
-    float du[D];
+    auto load_qrow = [&](int t, float (&v)[D]) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) v[d] = __ldg(qp + (int64_t)t * D + d);
+    };
+    // the separator this side faces (none at the ends of the path: coupling 0); the up lane also writes ITS x
+    float du[D], xsep[D], qsep[D], qmid[D];
+    const bool writes_sep = side == 0 && seg > 0;
     {
         float xs[LY::DQ];
 #pragma unroll
         for (int d = 0; d < LY::DQ; ++d) xs[d] = 0.f;
         const int js = side == 0 ? seg - 1 : seg;  // separator index 0 .. S-2
         if (js >= 0 && js < geo.S - 1) ld_lane<LY::XV>(xg + js * LY::x_f4(), xs);
+        load_qrow(writes_sep ? geo.sep(seg) : mid, qsep);  // both q rows are needed at the END of the chains only
+        load_qrow(mid, qmid);
 #pragma unroll
-        for (int d = 0; d < D; ++d) du[d] = xs[d];
+        for (int d = 0; d < D; ++d) du[d] = xsep[d] = xs[d];
     }
     // corrected right-hand sides: du_t = S_t^-1 (beta . du_{t-1}),  u_t += du_t
     float nS[NT], u[D];
@@ -483,10 +507,6 @@ lm_seg_substitute_kernel(const float* __restrict__ q, int64_t P, SegGeom geo, co
 
     // first back-substitution block and q row on their way while the middle block is factorised
     float qn[D], qn2[D];
-    auto load_qrow = [&](int t, float (&v)[D]) {
-#pragma unroll
-        for (int d = 0; d < D; ++d) v[d] = __ldg(qp + (int64_t)t * D + d);
-    };
     if (n_side > 0) {
         ld_lane<NV>(facg + t_of(n_side - 1) * LY::blk_f4(), nxt);  // own stores: same-thread ordering
         load_qrow(t_of(n_side - 1), qn);
@@ -514,10 +534,14 @@ lm_seg_substitute_kernel(const float* __restrict__ q, int64_t P, SegGeom geo, co
         sweep_neg_inverse<D>(Sm, dx, prm.pivot_floor);
         if (side == 0 && active) {
             float xn[D];
-            load_qrow(mid, xn);
 #pragma unroll
-            for (int i = 0; i < D; ++i) xn[i] += dx[i];
+            for (int i = 0; i < D; ++i) xn[i] = qmid[i] + dx[i];
             seg_store_x<M>(xo + (int64_t)mid * D, xn, prm.do_clamp);
+        }
+        if (writes_sep && active) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) qsep[i] += xsep[i];
+            seg_store_x<M>(xo + (int64_t)geo.sep(seg) * D, qsep, prm.do_clamp);
         }
     }
 
