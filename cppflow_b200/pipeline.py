@@ -253,7 +253,7 @@ class ResidentPipeline:
         if segments == "auto":
             # tools/probe_segpipe.py, ms per iteration at T = 300, twisted (default chunking) against 16 segments:
             #   256 paths 0.163 / 0.077   512: 0.171 / 0.093   1024: 0.197 / 0.139   2048: 0.280 / 0.227   4096: 0.372 / 0.42
-            segments = 16 if n_paths <= 1024 else 8 if n_paths <= 2048 else 0  # stand-alone solve at 2048: 0.149 (8) / 0.160 (16)
+            segments = 16 if n_paths <= 2048 else 0  # at 2048 paths in two chunks: 0.228 (16 segments) / 0.237 (8)
         self.segments = segments
         if n_chunks is None and segments:
             n_chunks = 1 if n_paths <= 256 else 2  # 512: 0.098 / 0.093 (1 / 2 chunks), 1024: 0.151 / 0.139, 2048: 0.262 / 0.229
