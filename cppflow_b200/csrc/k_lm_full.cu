@@ -1356,8 +1356,8 @@ static size_t ws_bytes(int64_t P, int64_t T, int flags = 0) {
 }
 
 template <class M>
-static int launch_solve_segmented(const SolveParams& sp, const float* q, int64_t P, int64_t T, int S, float* ws,
-                                  float* x_out, cudaStream_t st) {
+static int launch_solve_segmented(const SolveParams& sp, const float* q, int64_t P, int64_t T, int S, bool high_priority,
+                                  float* ws, float* x_out, cudaStream_t st) {
     unsigned char* base = reinterpret_cast<unsigned char*>(ws);
     size_t off = (ws_block_bytes<M>(P, T) + ws_tail_bytes(P) + 255) / 256 * 256;
     float* fac = reinterpret_cast<float*>(base + off);
@@ -1372,15 +1372,40 @@ static int launch_solve_segmented(const SolveParams& sp, const float* q, int64_t
         const char* e = std::getenv("CPPFLOW_SEG_PASSES");
         return e ? std::atoi(e) : 3;
     }();
-    lm_seg_eliminate_kernel<M, W><<<grid_for(warps, W), 32 * W, 0, st>>>(P, geo, sp, ws, fac, corners);
+    // CPPFLOW_LM_OVERLAP: the passes of one chunk run while another chunk's assembly fills the SMs; with the highest
+    // launch priority their single-warp CTAs take the registers of every assembly CTA that retires
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributePriority;
+    int least = 0, greatest = 0;
+    if (high_priority) cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    at[0].val.priority = greatest;
+    cfg.attrs = at;
+    cfg.numAttrs = high_priority ? 1 : 0;
+    cfg.stream = st;
+    auto launched = [](cudaError_t e, const char* what) {
+        return e == cudaSuccess ? CPPFLOW_OK : fail(CPPFLOW_E_CUDA, "%s launch: %s", what, cudaGetErrorString(e));
+    };
+    cfg.gridDim = dim3(grid_for(warps, W));
+    cfg.blockDim = dim3(32 * W);
+    cfg.dynamicSmemBytes = 0;
+    const float* ws_c = ws;
+    if (int rc = launched(cudaLaunchKernelEx(&cfg, lm_seg_eliminate_kernel<M, W>, P, geo, sp, ws_c, fac, corners), "lm_seg_eliminate")) return rc;
     if (passes < 2) return CPPFLOW_OK;
     const size_t sh = seg_reduced_smem<M::NDOF>(S);
     static SmemGrant granted;  // per template instantiation and device
     if (int rc = ensure_dynamic_smem(lm_seg_reduced_kernel<M>, seg_reduced_smem<M::NDOF>(SEG_MAX_SEGMENTS), granted)) return rc;
-    lm_seg_reduced_kernel<M><<<grid_for(P, 16), 32 * SEG_REDUCED_WARPS, sh, st>>>(P, geo, sp, ws, corners, sepx);
+    const float* corners_c = corners;
+    cfg.gridDim = dim3(grid_for(P, 16));
+    cfg.blockDim = dim3(32 * SEG_REDUCED_WARPS);
+    cfg.dynamicSmemBytes = sh;
+    if (int rc = launched(cudaLaunchKernelEx(&cfg, lm_seg_reduced_kernel<M>, P, geo, sp, ws_c, corners_c, sepx), "lm_seg_reduced")) return rc;
     if (passes < 3) return CPPFLOW_OK;
-    lm_seg_substitute_kernel<M, W><<<grid_for(warps, W), 32 * W, 0, st>>>(q, P, geo, sp, ws, fac, sepx, x_out);
-    return CPPFLOW_OK;
+    const float* sepx_c = sepx;
+    cfg.gridDim = dim3(grid_for(warps, W));
+    cfg.blockDim = dim3(32 * W);
+    cfg.dynamicSmemBytes = 0;
+    return launched(cudaLaunchKernelEx(&cfg, lm_seg_substitute_kernel<M, W>, q, P, geo, sp, ws_c, fac, sepx_c, x_out), "lm_seg_substitute");
 }
 
 template <class M>
@@ -1389,7 +1414,8 @@ static int launch_solve(const cppflow_lm_params* p, const float* q, int64_t P, i
     AssembleParams ap;
     SolveParams sp;
     make_params<M>(p, 0, flags & CPPFLOW_LM_CLAMP, ap, sp);
-    if (const int S = seg_count(T, flags)) return launch_solve_segmented<M>(sp, q, P, T, S, ws, x_out, st);
+    if (const int S = seg_count(T, flags))
+        return launch_solve_segmented<M>(sp, q, P, T, S, (flags & CPPFLOW_LM_OVERLAP) != 0, ws, x_out, st);
     if (P <= SOLVE_RESIDENT_MAX_PATHS && solve_resident_smem<M>(T) <= 200 * 1024) {
         const size_t sh = solve_resident_smem<M>(T);
         static SmemGrant granted;  // per template instantiation and device

@@ -34,6 +34,6 @@ for P in (256, 512, 1024, 2048, 4096):
     xs = x0[: P * T].contiguous(); xo = torch.empty_like(xs)
     out = {"paths": P, "twisted_default": step_ms(ResidentPipeline(problem, P, all_terms_parameters()), xs, xo)}
     for S in (8, 16):
-        for chunks in (1, 2, 4):
+        for chunks in (1, 2, 4, 8):
             out[f"S{S}_chunks{chunks}"] = step_ms(ResidentPipeline(problem, P, all_terms_parameters(), n_chunks=chunks, segments=S), xs, xo)
     print(json.dumps(out), flush=True)
