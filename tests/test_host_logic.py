@@ -320,3 +320,27 @@ def test_problem_rotational_path_length_discounts_the_clamp_floor():
     target[5:, 3], target[5:, 6] = math.cos(math.radians(5.0)), half  # one 10 degree turn about z
     p = Problem(DEFAULT_CONSTRAINTS, target, None, _FakeRobot(), "line", "fake__line", [], [], [], [])
     assert p.path_length_cumulative_rotational_change_deg == pytest.approx(10.0, abs=2e-2)
+
+
+def test_segmented_solve_model_equals_dense_solve():
+    """The algebra of csrc/lm_segsolve.cuh (segments between separator waypoints eliminated up and down, the separators'
+    reduced block-tridiagonal system with full couplings K = -beta Q, right-hand-side correction + twisted
+    back-substitution inside the segments), restated in fp64 numpy (tools/segsolve_model.py), against a dense solve of
+    the same SPD block-tridiagonal system - including one-block segments, a single segment, and the separator rule
+    s_j = floor(j T / S) the kernels use."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from segsolve_model import dense, segments, solve_segmented
+
+    rng = np.random.default_rng(7)
+    for T, S, D in [(300, 16, 8), (37, 5, 7), (9, 4, 8), (300, 2, 8), (20, 1, 7), (8, 4, 8), (64, 16, 7)]:
+        J = rng.normal(size=(T, 12, D))
+        beta = np.abs(rng.normal(size=D)) + 0.5
+        A = np.einsum("tki,tkj->tij", J, J) + 0.01 * np.eye(D) + 2 * np.diag(beta ** 2)
+        b = rng.normal(size=(T, D))
+        seps, segs = segments(T, S)
+        assert len(seps) == S - 1 and all(e >= a for a, e in segs) and segs[0][0] == 0 and segs[-1][1] == T - 1
+        assert sum(e - a + 1 for a, e in segs) + len(seps) == T
+        np.testing.assert_allclose(solve_segmented(A, b, beta, S), dense(A, b, beta), atol=1e-12)
