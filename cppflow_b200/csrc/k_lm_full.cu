@@ -1402,6 +1402,24 @@ static int launch_solve_segmented(const SolveParams& sp, const float* q, int64_t
     if (int rc = launched(cudaLaunchKernelEx(&cfg, lm_seg_reduced_kernel<M>, P, geo, sp, ws_c, corners_c, sepx), "lm_seg_reduced")) return rc;
     if (passes < 3) return CPPFLOW_OK;
     const float* sepx_c = sepx;
+    // pass 3 out of shared memory when a half-segment's factors fit (T / S <= ~70): every load in flight at once
+    int half = 0;
+    for (int sgm = 0; sgm < S; ++sgm) {
+        const int len = geo.last(sgm) - geo.first(sgm) + 1;
+        half = len / 2 > half ? len / 2 : half;
+    }
+    const size_t stage_bytes = (size_t)(half > 0 ? half : 1) * seg_stage_floats<M::NDOF>() * sizeof(float);
+    static const bool no_stage = std::getenv("CPPFLOW_SEG_NO_STAGE") != nullptr;  // A/B switch (tools/probe_segsolve.py)
+    if (stage_bytes <= 200 * 1024 && !no_stage) {
+        static SmemGrant granted3;  // per template instantiation and device
+        if (int rc = ensure_dynamic_smem(lm_seg_substitute_staged_kernel<M>, 200 * 1024, granted3)) return rc;
+        const float* fac_c = fac;
+        cfg.gridDim = dim3((unsigned)warps);
+        cfg.blockDim = dim3(32);
+        cfg.dynamicSmemBytes = stage_bytes;
+        return launched(cudaLaunchKernelEx(&cfg, lm_seg_substitute_staged_kernel<M>, q, P, geo, sp, ws_c, fac_c, sepx_c, x_out),
+                        "lm_seg_substitute_staged");
+    }
     cfg.gridDim = dim3(grid_for(warps, W));
     cfg.blockDim = dim3(32 * W);
     cfg.dynamicSmemBytes = 0;

@@ -576,4 +576,170 @@ lm_seg_substitute_kernel(const float* __restrict__ q, int64_t P, SegGeom geo, co
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// pass 3, staged: the steps of pass 3 are light (one matrix-vector product), so with registers only two blocks can be
+// requested ahead and at >= 256 paths every step waits for its block (ncu: 70 % of the samples on the long scoreboard).
+// Here a warp gathers the factors AND q rows of its whole half-segment into shared memory with cp.async at the start
+// (every load of the pass in flight at once), runs the du chain, the middle block and the back-substitution out of
+// shared memory (the corrected right-hand sides never go back to global memory), and reads the factor area once instead
+// of twice.  One single-warp CTA per (16-path group, segment); shared memory = ceil(L / 2) x (NW + DQ) x 32 lanes.
+template <int D>
+constexpr int seg_stage_floats() { return (BlockLayout<D>::NW + (D + 3) / 4 * 4) * 32; }  // per step of a half-segment
+
+template <class M>
+__global__ void __launch_bounds__(32, 1)
+lm_seg_substitute_staged_kernel(const float* __restrict__ q, int64_t P, SegGeom geo, const SolveParams prm,
+                                const float* __restrict__ ws, const float* __restrict__ fac,
+                                const float* __restrict__ sepx, float* __restrict__ x_out) {
+    constexpr int D = M::NDOF;
+    using LY = SegLayout<D>;
+    constexpr int NT = LY::NT, NW = LY::NW, NV = LY::NV, DQ = LY::DQ;
+    constexpr int STAGE = seg_stage_floats<D>();
+    extern __shared__ __align__(16) float seg_sm[];
+    const int lane = threadIdx.x;
+    const int64_t w = blockIdx.x;
+    const int64_t g = w / geo.S;
+    const int seg = (int)(w - g * geo.S);
+    const int side = lane & 1, l = lane >> 1;
+    const int64_t p_raw = g * 16 + l;
+    const bool active = p_raw < P;
+    const int64_t p = active ? p_raw : P - 1;
+    const int a = geo.first(seg), e = geo.last(seg);
+    const int L = e - a + 1, mid = a + L / 2;
+    const int n_side = side == 0 ? mid - a : e - mid;
+    const float4* wsg = reinterpret_cast<const float4*>(ws) + g * geo.T * LY::blk_f4() + l;
+    const float4* facg = reinterpret_cast<const float4*>(fac) + g * geo.T * LY::blk_f4() + l;
+    const float4* xg = reinterpret_cast<const float4*>(sepx) + g * (geo.S - 1) * LY::x_f4() + l;
+    const float* qp = q + p * geo.T * D;
+    float* xo = x_out + p * geo.T * D;
+    const BetaSel<M> bs(prm.b_rev, prm.b_pri);
+    auto t_of = [&](int k) { return side == 0 ? a + k : e - k; };
+    // step k of this lane: floats [f][lane] at seg_sm + k * STAGE; f < NW the factor block, then the q row
+    auto gather = [&](int k) {
+        const float4* src = facg + t_of(k) * LY::blk_f4();
+#pragma unroll
+        for (int f = 0; f < NV; ++f) cp_async16(reinterpret_cast<float4*>(seg_sm + k * STAGE) + f * 32 + lane, src + f * 16);
+        const float* qr = qp + (int64_t)t_of(k) * D;
+        if constexpr (D % 4 == 0) {
+#pragma unroll
+            for (int d = 0; d < D; d += 4)
+                cp_async16(reinterpret_cast<float4*>(seg_sm + k * STAGE + NW * 32) + (d / 4) * 32 + lane, qr + d);
+        } else {
+#pragma unroll
+            for (int d = 0; d < D; ++d) cp_async4(seg_sm + k * STAGE + NW * 32 + (d / 4) * 128 + lane * 4 + (d & 3), qr + d);
+        }
+    };
+    // float f of this lane's block at step k (blocks are stored as float4 [f / 4][lane])
+    auto at = [&](int k, int f) -> float& { return seg_sm[k * STAGE + (f >> 2) * 128 + lane * 4 + (f & 3)]; };
+
+    // first two steps in one group (the du chain starts on them), the rest in a second
+    for (int k = 0; k < n_side && k < 2; ++k) gather(k);
+    cp_async_commit();
+    for (int k = 2; k < n_side; ++k) gather(k);
+    cp_async_commit();
+
+    auto load_qrow = [&](int t, float (&v)[D]) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) v[d] = __ldg(qp + (int64_t)t * D + d);
+    };
+    float du[D], xsep[D], qsep[D], qmid[D], bmid[NW];
+    const bool writes_sep = side == 0 && seg > 0;
+    {
+        float xs[DQ];
+#pragma unroll
+        for (int d = 0; d < DQ; ++d) xs[d] = 0.f;
+        const int js = side == 0 ? seg - 1 : seg;  // separator index 0 .. S-2
+        if (js >= 0 && js < geo.S - 1) ld_lane<LY::XV>(xg + js * LY::x_f4(), xs);
+        ld_lane<NV>(wsg + (int64_t)mid * LY::blk_f4(), bmid);  // (A, b) of the middle block: needed after the du chain
+        load_qrow(writes_sep ? geo.sep(seg) : mid, qsep);
+        load_qrow(mid, qmid);
+#pragma unroll
+        for (int d = 0; d < D; ++d) du[d] = xsep[d] = xs[d];
+    }
+    auto read_block = [&](int k, float (&v)[NW]) {
+        const float4* src = reinterpret_cast<const float4*>(seg_sm + k * STAGE) + lane;
+#pragma unroll
+        for (int f = 0; f < NV; ++f) {
+            const float4 x4 = src[f * 32];
+            v[4 * f] = x4.x; v[4 * f + 1] = x4.y; v[4 * f + 2] = x4.z; v[4 * f + 3] = x4.w;
+        }
+    };
+
+    float nS[NT], u[D];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) nS[k] = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) u[d] = du[d];
+    cp_async_wait<1>();
+    __syncwarp();
+    for (int k = 0; k < n_side; ++k) {
+        if (k == 2) cp_async_wait<0>();  // a lane only reads what its own cp.async wrote: no warp barrier (the two
+                                         // lanes of a pair may leave this loop one step apart)
+        float blk[NW];
+        read_block(k, blk);
+        float z[D], y[D];
+        static_for<D>([&](auto Ii) {
+            constexpr int i = decltype(Ii)::value;
+            z[i] = bs.template b<i>() * du[i];
+        });
+        neg_symv<D>(blk, z, y);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            du[d] = y[d];
+            u[d] = blk[NT + d] + y[d];
+            at(k, NT + d) = u[d];  // the corrected right-hand side, for the back-substitution
+        }
+#pragma unroll
+        for (int i = 0; i < NT; ++i) nS[i] = blk[i];
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+
+    float dx[D];
+    {
+        float Sm[NT];
+        static_for<D>([&](auto Ii) {
+            constexpr int i = decltype(Ii)::value;
+            const float uo = __shfl_xor_sync(0xffffffffu, u[i], 1);
+            dx[i] = fmaf(bs.template b<i>(), u[i] + uo, bmid[NT + i]);
+            static_for<i + 1>([&](auto Jj) {
+                constexpr int j = decltype(Jj)::value;
+                const float so = __shfl_xor_sync(0xffffffffu, nS[tri(i, j)], 1);
+                Sm[tri(i, j)] = fmaf(bs.template bb<i, j>(), nS[tri(i, j)] + so, bmid[tri(i, j)]);
+            });
+        });
+        sweep_neg_inverse<D>(Sm, dx, prm.pivot_floor);
+        if (side == 0 && active) {
+            float xn[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) xn[i] = qmid[i] + dx[i];
+            seg_store_x<M>(xo + (int64_t)mid * D, xn, prm.do_clamp);
+        }
+        if (writes_sep && active) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) qsep[i] += xsep[i];
+            seg_store_x<M>(xo + (int64_t)geo.sep(seg) * D, qsep, prm.do_clamp);
+        }
+    }
+
+    for (int k = n_side - 1; k >= 0; --k) {
+        float blk[NW], xn[D];
+        read_block(k, blk);
+#pragma unroll
+        for (int d = 0; d < D; ++d) xn[d] = at(k, NW + d);
+        float z[D], y[D];
+        static_for<D>([&](auto Ii) {
+            constexpr int i = decltype(Ii)::value;
+            z[i] = bs.template b<i>() * dx[i];
+        });
+        neg_symv<D>(blk, z, y);
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            dx[i] = blk[NT + i] + y[i];
+            xn[i] += dx[i];
+        }
+        if (active) seg_store_x<M>(xo + (int64_t)t_of(k) * D, xn, prm.do_clamp);
+    }
+}
+
 }  // namespace cppflow
