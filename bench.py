@@ -497,6 +497,33 @@ def main():
     e2e_serial_ms = max_over_ranks(e0.elapsed_time(e1)) / e2e_steps
     h2d = x_host.numel() * 4
     d2h = out_host.numel() * 4
+    # the box's own floor for that traffic: the same two pinned buffers copied in and out at once on two streams, no
+    # kernels (every rank at the same time: the ranks share the host's memory system) - the e2e figure is PCIe-bound and
+    # moves with the box (1.64 to 2.2 ms seen), so the line carries its denominator
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    d_in, d_out = torch.empty_like(x0), torch.empty_like(x0)
+
+    def raw_copies(n):
+        for _ in range(n):
+            with torch.cuda.stream(s_in):
+                d_in.copy_(x_host, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                out_host.copy_(d_out, non_blocking=True)
+        torch.cuda.current_stream(dev).wait_stream(s_in)
+        torch.cuda.current_stream(dev).wait_stream(s_out)
+
+    raw_copies(2)
+    barrier()
+    s_in.wait_stream(torch.cuda.current_stream(dev))
+    s_out.wait_stream(torch.cuda.current_stream(dev))
+    e0.record()
+    s_in.wait_event(e0)
+    s_out.wait_event(e0)
+    raw_copies(e2e_steps)
+    e1.record()
+    barrier()
+    raw_copy_ms = max_over_ranks(e0.elapsed_time(e1)) / e2e_steps
+    del d_in, d_out
 
     # ---- the same iteration on ONE stream (assembly and solve back to back), for comparison
     n_single = max(5, min(steps, 100))
@@ -736,7 +763,8 @@ def main():
                 "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": wall / e2e_steps * 1e3, "steps": e2e_steps,
                 "api": "cppflow_b200.pipeline.HostPipeline.refine_async(host x -> host x_new), pinned host buffers, "
                        "independent steps two deep in flight",
-                "ms_per_step_one_at_a_time": e2e_serial_ms},
+                "ms_per_step_one_at_a_time": e2e_serial_ms,
+                "raw_duplex_copy_ms_per_step": raw_copy_ms, "frac_of_raw_copy": raw_copy_ms / (e2e_ms / e2e_steps)},
         "gpu_launches": steps * 2 * len(rpipe.chunks) + len(rpipe.chunks) + 1,  # K x (assemble + solve) per chunk, metrics per chunk, key + argmin
         "ms_per_step_without_tail": ms_steps_only,
         "single_stream_ms_per_step": ms_single,
