@@ -11,13 +11,15 @@
 //       [M^-1]_ee = S_e(up)^-1, [M^-1 b]_e = u_e(up), [M^-1]_aa = S_a(down)^-1, [M^-1 b]_a = u_a(down), and the up lane
 //       also carries Q = prod_t (S_t^-1 beta), so that [M^-1]_ae beta = Q.  The factors (-S_t^-1, u_t) of the lower
 //       half (up lane) and of the upper half (down lane) go to the factor area for pass 3.
-//   pass 2 (one lane per path; chain = S - 1): the separators' own block-tridiagonal system
+//   pass 2 (one CTA per 16 paths; chain = (S - 1) / 2): the separators' own block-tridiagonal system
 //       (A_s + beta (nS_left + nS_right) beta) x_s + K_{j-1}^T x_{s_{j-1}} + K_j x_{s_{j+1}} = b_s + beta (u_left + u_right),
-//       K_j = -beta Q(segment j + 1) (a full D x D block), by block Thomas.
+//       K_j = -beta Q(segment j + 1) (a full D x D block), built in shared memory by all warps and solved by a twisted
+//       block Thomas (two lanes per path), the coupling products of a step one column per warp.
 //   pass 3 (one lane pair per (path, segment); chain = L / 2 light steps + one sweep + L / 2 light steps):
 //       with x at both separators known, the stored right-hand sides are corrected (du_t = S_t^-1 beta du_{t-1}, a
 //       matrix-vector chain starting at the separator's x), the segment's middle block is solved exactly like the
-//       twisted solve's, and the back-substitution runs outwards from it.
+//       twisted solve's, and the back-substitution runs outwards from it.  Default variant: the half-segment's factors
+//       and q rows gathered into shared memory once with cp.async (lm_seg_substitute_staged_kernel).
 //
 // Same arithmetic kernels (sweep_neg_inverse, the beta-folded updates); the result differs from the twisted solve's
 // by rounding only (another elimination order), and depends on S but NOT on the path count, the chunking or the
