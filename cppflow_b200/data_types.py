@@ -324,6 +324,7 @@ class PathReport:
     min_self_distance_m: float
     min_env_distance_m: float
     is_valid: bool
+    initial_q_norm_dist: float = 0.0  # data_types.py:236-241: 0 when the problem has no initial configuration
 
     # the names the reference's Plan gives the same quantities (data_types.py:133-215)
     @property

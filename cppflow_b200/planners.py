@@ -274,7 +274,11 @@ def report_from_qpath(qpath: torch.Tensor, problem: Problem) -> PathReport:
     c = problem.constraints
     valid = (m[0] < c.max_allowed_position_error_cm and m[1] < c.max_allowed_rotation_error_deg
              and m[2] < c.max_allowed_mjac_deg and m[3] < c.max_allowed_mjac_cm and m[5] >= 0 and m[6] >= 0)
-    return PathReport(qpath, m[0], m[1], m[2], m[3], m[4], m[5], m[6], bool(valid))
+    dist = 0.0
+    if problem.initial_configuration is not None:  # part of Plan.is_valid in the reference (data_types.py:245)
+        dist = float(torch.norm(problem.initial_configuration.to(qpath.device) - qpath[0]))
+        valid = valid and dist < SUCCESS_THRESHOLD_initial_q_norm_dist
+    return PathReport(qpath, m[0], m[1], m[2], m[3], m[4], m[5], m[6], bool(valid), dist)
 
 
 class Planner:

@@ -344,3 +344,27 @@ def test_segmented_solve_model_equals_dense_solve():
         assert len(seps) == S - 1 and all(e >= a for a, e in segs) and segs[0][0] == 0 and segs[-1][1] == T - 1
         assert sum(e - a + 1 for a, e in segs) + len(seps) == T
         np.testing.assert_allclose(solve_segmented(A, b, beta, S), dense(A, b, beta), atol=1e-12)
+
+
+def test_latent_sampling_layout():
+    """tests/planners_test.py:219-260 (`_get_fixed_random_latent`, per-k): [k * T, width] latents, one latent per path
+    repeated over its T waypoints, k distinct ones; uniform in +-scale / 2 or gaussian; sampling near a centre latent keeps
+    the centre as the first path's latent (planners.py:136-153)."""
+    from cppflow_b200.planners import LatentIkCandidateGenerator
+
+    k, T, width = 15, 300, 9
+    for dist in ("uniform", "gaussian"):
+        gen = LatentIkCandidateGenerator(seed=4, latent_distribution=dist, latent_vector_scale=1.5)
+        latent = gen._sample_latents(k, T, width)
+        assert latent.shape == (k * T, width)
+        per_path = latent.reshape(k, T, width)
+        assert torch.equal(per_path, per_path[:, :1].expand(k, T, width)), "a path's latent changes along the path"
+        assert per_path[:, 0].unique(dim=0).shape[0] == k, "paths share a latent"
+        if dist == "uniform":
+            assert latent.min() >= -0.75 and latent.max() <= 0.75
+            assert latent.min() < -0.6 and latent.max() > 0.6 and abs(float(latent.mean())) < 0.1
+    gen = LatentIkCandidateGenerator(seed=4, latent_vector_scale=1.0)
+    centre = torch.linspace(-0.3, 0.3, 7)
+    near = gen._sample_latents_near(5, 11, centre).reshape(5, 11, 7)
+    assert torch.equal(near[0], centre.expand(11, 7))
+    assert ((near - centre).abs() <= 0.5 + 1e-6).all() and near[1:, 0].unique(dim=0).shape[0] == 4
