@@ -304,3 +304,20 @@ def test_use_initial_configuration():
     dist = float(torch.norm(plan.q_path[0] - q0))
     assert dist < 0.1 * SUCCESS_THRESHOLD_initial_q_norm_dist, dist
     assert abs(plan.initial_q_norm_dist - dist) < 1e-6
+
+
+def test_joint_limit_avoidance():
+    """tests/search_test.py:59-75: the path `PlannerSearcher` returns for tests/fetch__s__truncated.yaml (k = 20) stays a
+    degree away from every joint limit - dp_search's joint-limit penalty (search.py:25-52) at work."""
+    from cppflow_b200.data_types import PlannerSettings
+    from cppflow_b200.planners import LatentIkCandidateGenerator, PlannerSearcher
+
+    problem = _problem("fetch__s__truncated")
+    planner = PlannerSearcher(PlannerSettings(k=20, tmax_sec=5.0, anytime_mode_enabled=False, verbosity=0), problem.robot,
+                              LatentIkCandidateGenerator(seed=3))
+    plan = planner.generate_plan(problem).plan
+    assert plan.q_path.shape == (problem.n_timesteps, problem.robot.ndof)
+    eps = float(np.deg2rad(1))
+    for joint_idx, (lo, hi) in enumerate(problem.robot.actuated_joints_limits):
+        assert not (plan.q_path[:, joint_idx] < lo + eps).any(), joint_idx
+        assert not (plan.q_path[:, joint_idx] > hi - eps).any(), joint_idx

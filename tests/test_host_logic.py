@@ -368,3 +368,15 @@ def test_latent_sampling_layout():
     near = gen._sample_latents_near(5, 11, centre).reshape(5, 11, 7)
     assert torch.equal(near[0], centre.expand(11, 7))
     assert ((near - centre).abs() <= 0.5 + 1e-6).all() and near[1:, 0].unique(dim=0).shape[0] == 4
+
+
+def test_mjac_consistency():
+    """tests/evaluation_utils_test.py:12-15: the three ways the reference computes the maximum joint-angle change of a
+    path agree (evaluation_utils.py:113-141)."""
+    from cppflow_b200.evaluation_utils import angular_changes, calculate_mjac_deg, calculate_per_timestep_mjac_deg
+
+    torch.manual_seed(0)
+    qpath = torch.randn((10, 3)) * 3.0  # beyond +-pi: the wrap matters
+    assert calculate_mjac_deg(qpath) == pytest.approx(float(calculate_per_timestep_mjac_deg(qpath).max()), abs=1e-5)
+    assert calculate_mjac_deg(qpath) == pytest.approx(float(torch.rad2deg(angular_changes(qpath).abs().max())), abs=1e-5)
+    assert calculate_per_timestep_mjac_deg(qpath).shape == (9,)
