@@ -636,3 +636,36 @@ def test_segmented_solve_equals_twisted_solve_up_to_rounding(robots, r):
             lim = torch.tensor(rob.actuated_joints_limits, device=DEV, dtype=torch.float32)
             assert torch.equal(clamped, torch.minimum(torch.maximum(unclamped, lim[:, 0]), lim[:, 1]))
     print("segmented / twisted, worst ratios:", r, {k: round(v, 2) for k, v in worst.items()})
+
+
+def test_resident_pipeline_segmented_solve_is_chunking_independent(robots):
+    """`ResidentPipeline(segments=...)`: for a given segment count the refined paths do not depend on the chunk count, on
+    eager enqueue or graph replay, and equal the single-launch step with the same segment count bit for bit;
+    `segments="auto"` takes 16 segments up to 2048 paths and the twisted solve above."""
+    from cppflow_b200 import ops
+    from cppflow_b200.lm_hyper_parameters import all_terms_parameters
+    from cppflow_b200.pipeline import ResidentPipeline
+    from cppflow_b200.synthetic import synthetic_problem as device_problem, synthetic_seeds_host
+
+    robot, T = robots["fetch"], 61
+    problem = device_problem(robot, T, seed=0, device=DEV)
+    prm = ops.make_params(all_terms_parameters())
+    P = 700  # ragged: not a multiple of 16 x chunks
+    x = synthetic_seeds_host(robot, P, T, seed=0)[1].to(DEV)
+    for S in (4, 15):
+        ref = ops.lm_full_step(robot.robot_id, robot.ndof, prm, x, None, problem.target_path, P, T, problem.obstacle_tables,
+                               True, segments=S)
+        for n_chunks in (1, 2, 5):
+            pipe = ResidentPipeline(problem, P, all_terms_parameters(), n_chunks=n_chunks, segments=S)
+            out_e, out_g = torch.full_like(x, float("nan")), torch.full_like(x, float("nan"))
+            pipe.begin(); pipe.enqueue_step(x, out_e); pipe.end()
+            graph = pipe.capture(lambda: pipe.enqueue_step(x, out_g))
+            graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(out_e, ref), (S, n_chunks, float((out_e - ref).abs().max()))
+            assert torch.equal(out_g, ref), (S, n_chunks, "graph replay")
+    assert ResidentPipeline(problem, 2048, all_terms_parameters(), segments="auto").segments == 16
+    assert ResidentPipeline(problem, 2049, all_terms_parameters(), segments="auto").segments == 0
+    twisted = ops.lm_full_step(robot.robot_id, robot.ndof, prm, x, None, problem.target_path, P, T, problem.obstacle_tables, True)
+    assert not torch.equal(twisted, ref)  # another elimination order: rounding-level differences, not the same bits
+    assert float((twisted - ref).abs().max()) < 0.2
