@@ -669,3 +669,26 @@ def test_resident_pipeline_segmented_solve_is_chunking_independent(robots):
     twisted = ops.lm_full_step(robot.robot_id, robot.ndof, prm, x, None, problem.target_path, P, T, problem.obstacle_tables, True)
     assert not torch.equal(twisted, ref)  # another elimination order: rounding-level differences, not the same bits
     assert float((twisted - ref).abs().max()) < 0.2
+
+
+@pytest.mark.parametrize("P,T,S", [(3, 1000, 32), (2, 4000, 32), (40, 129, 255), (16, 4000, 7)])
+def test_segmented_solve_long_paths(robots, P, T, S):
+    """Long paths: half-segments that fit the staged pass 3's shared memory (T = 1000, 32 segments) and ones that do not
+    (T = 4000: the streaming pass 3), a segment count above the cap of 32 / T / 4, few long segments.  With the
+    well-conditioned differencing parameter set the segmented and the twisted step agree element-wise."""
+    from cppflow_b200 import ops
+    from cppflow_b200.lm_hyper_parameters import ALT_LOSS_V2_1_DIFF
+
+    rob = robots["panda"]
+    cuboids, Tcuboids = cuboid_tensors(OBSTACLES["panda"])
+    ob = ops.Obstacles(cuboids, Tcuboids)
+    m, target, x0 = synthetic_problem("panda", P, T, seed=P + T)
+    x, tg = x0.to(DEV), target.to(DEV)
+    prm = ops.make_params(ALT_LOSS_V2_1_DIFF)
+    ref = ops.lm_full_step(rob.robot_id, rob.ndof, prm, x, None, tg, P, T, ob, True)
+    got = ops.lm_full_step(rob.robot_id, rob.ndof, prm, x, None, tg, P, T, ob, True, segments=S)
+    assert torch.isfinite(got).all()
+    step = float((ref - x).abs().max())
+    err = float((got - ref).abs().max())
+    assert err < 1e-4 + 1e-3 * step, (P, T, S, err, step)
+    assert not torch.equal(got, ref) or step == 0.0  # it IS another solve
