@@ -110,3 +110,54 @@ def test_planning_query_end_to_end():
     q0 = cand[int(torch.nonzero(hit)[0])].cpu().tolist()
     refused = svc.planning_query(_query(wp, tmax=30.0, q0=q0), NS())
     assert refused.is_malformed_query and refused.malformed_query_error == "Initial configuration is in collision with environment"
+
+
+def test_publisher_request_builders():
+    """cppflow/ros2/ros2_publisher.py:56-136: the example client's two requests, built without a transport."""
+    from cppflow_b200.ros2.ros2_publisher import build_dummy_query, build_environment_request, describe_response, dummy_target_path
+
+    env = build_environment_request()
+    assert (env.jrl_robot_name, env.end_effector_frame, env.base_frame, env.obstacles) == ("panda", "panda_hand", "panda_link0", [])
+    rows = dummy_target_path()
+    assert len(rows) == 11 and rows[0][:3] == pytest.approx([0.45, 0.5421984559194368, 0.7885155964931997])
+    q = build_dummy_query([0.1] * 7)
+    assert len(q.problems) == 1 and len(q.problems[0].waypoints) == 11
+    assert q.initial_configuration_is_set and q.initial_configuration.position == [0.1] * 7
+    assert (q.max_allowed_position_error_cm, q.max_allowed_rotation_error_deg, q.max_allowed_mjac_deg, q.max_allowed_mjac_cm,
+            q.max_planning_time_sec, q.anytime_mode_enabled) == (0.1, 1.0, 2.5, 0.5, 3.0, False)
+    se3 = waypoints_to_se3_sequence(q.problems[0].waypoints)
+    assert torch.allclose(se3, torch.tensor(rows))
+    assert not build_dummy_query(None).initial_configuration_is_set
+    resp = NS(trajectories=[NS(joint_names=["a"], points=[NS(positions=[1.0])])], success=[True], errors=[""])
+    assert describe_response(resp) == ["Received CppFlowQuery.Response", "Problem 0: Success = True, Error = ",
+                                       "Trajectory 0: ['a'], 1 points", "  0: [1.0]"]
+    svc = CppFlowQueryService(device="cpu")
+    assert svc.environment_setup(env, NS()).success is True  # the example's scene request is accepted as it is
+
+
+@pytest.mark.gpu
+def test_publisher_example_through_the_service():
+    """The reference's example session (ros2 run cppflow ros2_subscriber / ros2_publisher) without ROS2: scene
+    configuration for the Panda, an initial configuration that reaches the first waypoint to 5e-5 m without
+    self-collision, the 11-waypoint query; the service answers with a valid 11-point trajectory that starts at the
+    requested configuration."""
+    from cppflow_b200.robot import get_robot
+    from cppflow_b200.ros2.ros2_publisher import (build_dummy_query, build_environment_request, describe_response,
+                                                  dummy_target_path, get_initial_configuration)
+
+    dev = "cuda:0"
+    svc = CppFlowQueryService(device=dev)
+    assert svc.environment_setup(build_environment_request(), NS()).success is True
+    robot = get_robot("panda")
+    with pytest.warns(UserWarning):
+        q0 = get_initial_configuration(robot, dummy_target_path()[0], device=dev)
+    pose = robot.forward_kinematics(torch.tensor([q0], device=dev))[0].cpu()
+    assert float((pose[:3] - torch.tensor(dummy_target_path()[0][:3])).norm()) < 5e-5
+    resp = svc.planning_query(build_dummy_query(q0), NS(is_malformed_query=False, malformed_query_error=""))
+    assert not resp.is_malformed_query, resp.malformed_query_error
+    assert resp.success == [True], resp.errors
+    traj = resp.trajectories[0]
+    assert len(traj.points) == 11 and traj.joint_names == robot.actuated_joint_names
+    start = torch.tensor(traj.points[0].positions)
+    assert float((start - torch.tensor(q0)).norm()) < 0.02
+    assert describe_response(resp)[1] == "Problem 0: Success = True, Error = "
